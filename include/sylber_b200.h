@@ -1,0 +1,109 @@
+/* sylber_b200 - C ABI of the B200-native Segmenter forward path.
+ *
+ * The reference (Berkeley-Speech-Group/sylber) has no FFI: its boundary is Python-level, three calls inside
+ * Segmenter.__call__ (sylber/model/sylber.py:63-138):
+ *     :122  self.speech_model(batch_tensor, attention_mask=...).last_hidden_state      -> syl_forward (hidden)
+ *     :126  get_segment(states, norm_threshold, merge_threshold)                       -> syl_forward (seg, seg_count)
+ *     :133  states[s:e].mean(0)                                                        -> syl_forward (seg_feat)
+ * and the weights enter through load_state_dict at :51-52                              -> syl_load_weight / syl_finalize.
+ * This header is what a ctypes / cffi binding on the reference side would bind (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every pointer argument named *_dev / wav / hidden / seg... is a DEVICE pointer on the handle's GPU unless
+ *     stated otherwise; the caller owns all of them, including the workspace.  The library owns only its packed
+ *     weights and never allocates per call.
+ *   - functions return 0 on success or a negative SYL_E_* code; nothing throws across the ABI; the message of the
+ *     last failure is available from syl_last_error().
+ *   - work is enqueued on the CUDA stream passed in (a cudaStream_t cast to void*); the library never
+ *     synchronises the device except inside syl_finalize().
+ *   - one handle per device, not thread safe.  There is no CPU fallback: without an sm_100 GPU every compute
+ *     entry point fails with SYL_E_CUDA.
+ */
+#ifndef SYLBER_B200_H
+#define SYLBER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct syl_handle syl_handle;
+
+#define SYL_OK 0
+#define SYL_E_ARG (-1)      /* bad argument / shape */
+#define SYL_E_STATE (-2)    /* called in the wrong state (e.g. forward before finalize, missing weight) */
+#define SYL_E_CUDA (-3)     /* CUDA runtime / driver failure */
+#define SYL_E_WORKSPACE (-4) /* workspace too small */
+
+/* precision mode = bit mask of the GEMM sites that run split precision (fp16 hi + lo operands, 3 tensor-core
+ * passes, ~fp32 accuracy) instead of a single fp16 pass.  DESIGN.md explains the measured error budget. */
+#define SYL_SPLIT_CONV 1     /* conv1..conv6 of the feature encoder (dominant error source) */
+#define SYL_SPLIT_PROJ 2     /* feature projection + positional conv */
+#define SYL_SPLIT_ENC 4      /* encoder linear layers (QKV, out-proj, FFN) */
+#define SYL_MODE_PARITY (SYL_SPLIT_CONV)                     /* default: meets 1e-3 rel vs the fp32 reference */
+#define SYL_MODE_FAST 0                                      /* single-pass fp16 everywhere */
+#define SYL_MODE_EXACT (SYL_SPLIT_CONV | SYL_SPLIT_PROJ | SYL_SPLIT_ENC)
+
+#define SYL_DTYPE_F32 0
+
+/* ---- lifecycle: replaces HubertModel(config) + load_state_dict (sylber/model/sylber.py:41,51-54) ---- */
+int syl_create(syl_handle** out, int device, int n_layers, int mode);
+/* name: HubertModel state_dict key; dev_ptr: fp32 device tensor, copied.  Both pos-conv namings are accepted
+ * (parametrizations.weight.original0/1 and weight_g/weight_v). */
+int syl_load_weight(syl_handle* h, const char* name, const void* dev_ptr, const int64_t* shape, int ndim, int dtype);
+/* folds weight-norm, packs GEMM operands; fails (SYL_E_STATE) naming the first missing tensor */
+int syl_finalize(syl_handle* h);
+void syl_destroy(syl_handle* h);
+const char* syl_last_error(const syl_handle* h);   /* h may be NULL: last error of syl_create */
+
+/* ---- shapes ---- */
+int syl_num_frames(int n_samples);                  /* HF _get_feat_extract_output_lengths (modeling_hubert.py:675-688) */
+size_t syl_workspace_bytes(const syl_handle* h, int batch, int t_samp_max);
+
+/* ---- the hot path: sylber/model/sylber.py:122-133 ----
+ *   wav        [batch, t_samp_max] fp32, zero padded              (sylber.py:93-117)
+ *   n_samples  [batch] int32, valid samples per utterance         (what the reference's attention_mask encodes)
+ *   hidden     [batch, T, 768] fp32 out, T = syl_num_frames(t_samp_max)     == last_hidden_state
+ *   seg        [batch, max_seg, 2] int32 out, frame indices [start, end)    == get_segment(...)
+ *   seg_count  [batch] int32 out (may exceed max_seg: then only the first max_seg rows were written)
+ *   seg_feat   [batch, max_seg, 768] fp32 out                               == states[s:e].mean(0)
+ * seg / seg_count / seg_feat may all be NULL to run the encoder only.
+ */
+int syl_forward(syl_handle* h, const float* wav, const int32_t* n_samples, int batch, int t_samp_max, float* hidden,
+                int32_t* seg, int32_t* seg_count, float* seg_feat, int max_seg, float thr_norm, float thr_merge,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- per-stage entry points (unit tests, ncu) ---- */
+/* conv feature encoder, modeling_hubert.py:203-213: wav -> [batch, T, 512] fp32 (channels last) */
+int syl_conv_frontend(syl_handle* h, const float* wav, int batch, int t_samp_max, float* feats, void* workspace,
+                      size_t workspace_bytes, void* stream);
+/* one post-LN encoder layer, modeling_hubert.py:388-405: h_in/h_out [batch, T, 768] fp32 */
+int syl_encoder_layer(syl_handle* h, int layer, const float* h_in, const int32_t* valid_frames, int batch, int T,
+                      float* h_out, void* workspace, size_t workspace_bytes, void* stream);
+/* attention core: qkv [batch*T, 2304] fp16 (Q pre-scaled by 1/8), out [batch*T, 768] fp16 */
+int syl_attention(const void* qkv_f16, const int32_t* kv_len, int batch, int T, void* out_f16, void* stream);
+/* segmentation + pooling on given states [batch, T, 768] fp32; workspace >= syl_segment_workspace_bytes */
+size_t syl_segment_workspace_bytes(int batch, int T);
+int syl_segment(const float* states, int batch, int T, float thr_norm, float thr_merge, int32_t* seg,
+                int32_t* seg_count, float* seg_feat, int max_seg, void* workspace, size_t workspace_bytes,
+                void* stream);
+/* generic tensor-core GEMM on fp32 inputs: out[M,N] = act(A[M,K] W[N,K]^T + bias) + residual */
+size_t syl_gemm_workspace_bytes(int M, int N, int K);
+int syl_gemm_f32(const float* A, const float* W, const float* bias, const float* residual, float* out, int M, int N,
+                 int K, int n_pass, int act, void* workspace, size_t workspace_bytes, void* stream);
+/* y[i] = powf(x[i], 0.5f) as glibc computes it (the fp64 replay used by the segmentation kernel) */
+int syl_powf_half(const float* x, float* y, int64_t n, void* stream);
+/* copy an intermediate of the most recent syl_forward / syl_conv_frontend out as fp32.
+ * names: conv0..conv6 ([batch, L_i, 512]), proj, pos, enc_in ([batch, T, 768]) */
+int syl_read_stage(syl_handle* h, const char* name, float* out, size_t n_floats, void* stream);
+/* run only the first n encoder layers in syl_forward (debug / per-layer parity); n < 0 restores all */
+int syl_set_active_layers(syl_handle* h, int n);
+/* how many kernels of this library syl_forward launches for the given shape (bench.py reports it) */
+int syl_forward_launch_count(const syl_handle* h, int with_segmentation);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SYLBER_B200_H */

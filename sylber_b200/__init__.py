@@ -1,0 +1,13 @@
+"""sylber_b200 - B200-native (sm_100a) implementation of SYLBER's `Segmenter` forward path.
+
+Drop-in for `sylber.Segmenter` (reference: sylber/model/sylber.py:28-138): same constructor, same
+`__call__(wav_file=None, wav=None, in_second=True)`, same `{segments, segment_features, hidden_states}`
+output contract.  All arithmetic runs in hand-written CUDA kernels behind the C ABI declared in
+include/sylber_b200.h (libsylber_b200.so); PyTorch is used for device memory, streams and
+torch.distributed only.  There is no CPU fallback.
+"""
+from .segmenter import Segmenter, SpeechModel  # noqa: F401
+from ._lib import build_library, load_library, library_path  # noqa: F401
+
+__all__ = ["Segmenter", "SpeechModel", "build_library", "load_library", "library_path"]
+__version__ = "0.1.0"

@@ -1,0 +1,100 @@
+"""ctypes binding of libsylber_b200.so (the C ABI in include/sylber_b200.h) and its nvcc build recipe."""
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_PKG, "csrc")
+_SO = os.path.join(_PKG, "libsylber_b200.so")
+
+SYL_SPLIT_CONV, SYL_SPLIT_PROJ, SYL_SPLIT_ENC = 1, 2, 4
+MODES = {
+    "parity": SYL_SPLIT_CONV,
+    "fast": 0,
+    "exact": SYL_SPLIT_CONV | SYL_SPLIT_PROJ | SYL_SPLIT_ENC,
+}
+
+_c_void_p, _c_int, _c_size_t, _c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_float
+
+# name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
+SIGNATURES = {
+    "syl_create": (_c_int, [ctypes.POINTER(_c_void_p), _c_int, _c_int, _c_int]),
+    "syl_load_weight": (_c_int, [_c_void_p, ctypes.c_char_p, _c_void_p, ctypes.POINTER(ctypes.c_int64), _c_int, _c_int]),
+    "syl_finalize": (_c_int, [_c_void_p]),
+    "syl_destroy": (None, [_c_void_p]),
+    "syl_last_error": (ctypes.c_char_p, [_c_void_p]),
+    "syl_num_frames": (_c_int, [_c_int]),
+    "syl_workspace_bytes": (_c_size_t, [_c_void_p, _c_int, _c_int]),
+    "syl_forward": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p,
+                             _c_void_p, _c_int, _c_float, _c_float, _c_void_p, _c_size_t, _c_void_p]),
+    "syl_conv_frontend": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
+    "syl_encoder_layer": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p,
+                                   _c_size_t, _c_void_p]),
+    "syl_attention": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p]),
+    "syl_segment_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
+    "syl_segment": (_c_int, [_c_void_p, _c_int, _c_int, _c_float, _c_float, _c_void_p, _c_void_p, _c_void_p, _c_int,
+                             _c_void_p, _c_size_t, _c_void_p]),
+    "syl_gemm_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
+    "syl_gemm_f32": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int,
+                              _c_int, _c_void_p, _c_size_t, _c_void_p]),
+    "syl_powf_half": (_c_int, [_c_void_p, _c_void_p, ctypes.c_int64, _c_void_p]),
+    "syl_read_stage": (_c_int, [_c_void_p, ctypes.c_char_p, _c_void_p, _c_size_t, _c_void_p]),
+    "syl_set_active_layers": (_c_int, [_c_void_p, _c_int]),
+    "syl_forward_launch_count": (_c_int, [_c_void_p, _c_int]),
+}
+
+_LIB = None
+
+
+def library_path() -> str:
+    return _SO
+
+
+def _sources():
+    return sorted(os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cu", ".cuh"))) + [
+        os.path.join(os.path.dirname(_PKG), "include", "sylber_b200.h")]
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/api.cu for sm_100a into sylber_b200/libsylber_b200.so (in-tree so it travels to the GPU box)."""
+    if not force and os.path.exists(_SO):
+        newest = max(os.path.getmtime(s) for s in _sources())
+        if os.path.getmtime(_SO) >= newest:
+            return _SO
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build libsylber_b200.so")
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+           "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177",
+           "-o", _SO, os.path.join(_CSRC, "api.cu")]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.check_call(cmd, cwd=_CSRC)
+    return _SO
+
+
+def load_library():
+    """Load the C-ABI library.  Raises if it has not been built - there is no fallback implementation."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(_SO):
+        raise RuntimeError(
+            f"{_SO} is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(needs nvcc); sylber_b200 has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(_SO)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def check(lib, handle, rc, what):
+    if rc != 0:
+        msg = lib.syl_last_error(handle)
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else 'unknown error'}")

@@ -1,0 +1,1050 @@
+// C ABI of libsylber_b200.so (declared in include/sylber_b200.h): weight packing, workspace planning,
+// TMA descriptor construction and the launch sequence of the Segmenter forward path
+// (sylber/model/sylber.py:122-133 -> transformers HubertModel.forward, get_segment, segment means).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/sylber_b200.h"
+#include "attention.cuh"
+#include "frontend.cuh"
+#include "gemm_tc.cuh"
+#include "segment.cuh"
+
+using namespace syl;
+
+namespace {
+
+constexpr int kConvK[7] = {10, 3, 3, 3, 3, 2, 2};
+constexpr int kConvS[7] = {5, 2, 2, 2, 2, 2, 2};
+constexpr int kC = 512;        // conv channels
+constexpr int kH = 768;        // hidden size
+constexpr int kHeads = 12;
+constexpr int kF = 3072;       // FFN size
+constexpr int kPosK = 128;
+constexpr int kPosG = 16;
+constexpr int kPosCg = 48;     // channels per group
+
+std::string g_create_error;
+
+// ------------------------------------------------------------------------------------------------
+// driver entry point for cuTensorMapEncodeTiled (no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// fp16 tensor map, up to 3 dims, 128B swizzle, box = {64, box1, 1}
+bool make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                   uint32_t box1, std::string* err) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    *err = "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)";
+    return false;
+  }
+  cuuint64_t gdim[3] = {1, 1, 1};
+  cuuint64_t gstr[2] = {0, 0};
+  cuuint32_t box[3] = {64, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) gdim[i] = dims[i];
+  for (int i = 1; i < rank; ++i) gstr[i - 1] = strides_elems[i] * 2;
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu strides %llu %llu box1 %u",
+             (int)r, rank, (unsigned long long)gdim[0], (unsigned long long)gdim[1], (unsigned long long)gdim[2],
+             (unsigned long long)gstr[0], (unsigned long long)gstr[1], box1);
+    *err = buf;
+    return false;
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small utility kernels (weight packing, dtype conversion)
+// ------------------------------------------------------------------------------------------------
+__global__ void split_f32_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo,
+                                 size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    __half h, l;
+    split_f16(in[i], h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
+__global__ void join_f16_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, float* __restrict__ out,
+                                size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __half2float(hi[i]) + (lo ? __half2float(lo[i]) : 0.0f);
+}
+
+// conv weight [co][ci][k] fp32 -> GEMM B operand [co][j*C + ci] fp16 hi/lo
+__global__ void pack_conv_w_kernel(const float* __restrict__ w, int k, __half* __restrict__ hi,
+                                   __half* __restrict__ lo) {
+  const size_t n = (size_t)kC * kC * k;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int ci = i % kC;
+    const int j = (i / kC) % k;
+    const int co = i / ((size_t)kC * k);
+    __half h, l;
+    split_f16(w[((size_t)co * kC + ci) * k + j], h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+// weight-norm denominator of the positional conv: norm over (out, in) for each tap (dim=2)
+__global__ void pos_tap_norm_kernel(const float* __restrict__ v, float* __restrict__ norm) {
+  __shared__ double red[256];
+  const int j = blockIdx.x;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < kH * kPosCg; i += blockDim.x) {
+    const double x = v[(size_t)i * kPosK + j];
+    s += x * x;
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) norm[j] = (float)sqrt(red[0]);
+}
+
+// pos conv weight v [co][ci(48)][j(128)], g [128] -> B operand [co][j*64 + ci] (ci padded to 64 with zeros)
+__global__ void pack_pos_w_kernel(const float* __restrict__ v, const float* __restrict__ g,
+                                  const float* __restrict__ norm, __half* __restrict__ hi, __half* __restrict__ lo) {
+  const size_t n = (size_t)kH * kPosK * 64;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int ci = i % 64;
+    const int j = (i / 64) % kPosK;
+    const int co = i / (64 * kPosK);
+    float w = 0.0f;
+    if (ci < kPosCg) w = v[((size_t)co * kPosCg + ci) * kPosK + j] * (g[j] / norm[j]);
+    __half h, l;
+    split_f16(w, h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+__global__ void valid_frames_kernel(const int32_t* __restrict__ n_samples, int batch, int T, int32_t* __restrict__ valid) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  int n = n_samples[b];
+  const int k[7] = {10, 3, 3, 3, 3, 2, 2}, s[7] = {5, 2, 2, 2, 2, 2, 2};
+  for (int i = 0; i < 7; ++i) n = (n >= k[i]) ? (n - k[i]) / s[i] + 1 : 0;
+  valid[b] = max(1, min(n, T));
+}
+
+__global__ void fill_i32_kernel(int32_t* p, int n, int v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+__global__ void powf_half_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = powf_half(x[i]);
+}
+
+inline int grid_for(size_t n, int block = 256) { return (int)std::min<size_t>((n + block - 1) / block, 148 * 16); }
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct PackedLinear {   // B operand [N][K] fp16 hi/lo + tensor maps + fp32 bias
+  __half* hi = nullptr;
+  __half* lo = nullptr;
+  float* bias = nullptr;
+  int N = 0, K = 0;
+  CUtensorMap map_hi, map_lo;
+};
+
+struct LayerW {
+  PackedLinear qkv, out, ffn1, ffn2;
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+};
+
+struct GemmOp {
+  CUtensorMap a_hi, a_lo;
+  const PackedLinear* w = nullptr;
+  GemmParams p;
+  int block_n = 256;
+};
+
+struct WsLayout {
+  size_t total = 0;
+  size_t mom, gn_scale, gn_shift, valid, nsq, seg_scratch;
+  size_t act_hi[6], act_lo[6], conv6;
+  size_t ln_hi, ln_lo, h, h16_hi, h16_lo, pos, pre, qkv, ctx_hi, ctx_lo, mid_hi, mid_lo;
+  int L[7];
+  int T;
+};
+
+struct Plan {
+  bool valid = false;
+  int batch = 0, t_samp = 0;
+  void* ws = nullptr;
+  float* hidden = nullptr;
+  WsLayout lay;
+  GemmOp conv[6];
+  GemmOp proj, pos;
+  std::vector<GemmOp> qkv, out, ffn1, ffn2;   // per layer (A maps are shared, params differ in weights)
+  CUtensorMap attn_map;
+};
+
+}  // namespace
+
+struct syl_handle {
+  int device = 0;
+  int n_layers = 9;
+  int active_layers = -1;
+  int mode = SYL_MODE_PARITY;
+  bool finalized = false;
+  std::string err;
+  std::map<std::string, std::pair<float*, std::vector<int64_t>>> raw;
+  std::vector<void*> owned;
+  // packed weights
+  float* conv0_w = nullptr;
+  float *gn_g = nullptr, *gn_b = nullptr;
+  PackedLinear convw[6];
+  float *fp_ln_g = nullptr, *fp_ln_b = nullptr;
+  PackedLinear proj;
+  PackedLinear pos;
+  float *enc_ln_g = nullptr, *enc_ln_b = nullptr;
+  std::vector<LayerW> layers;
+  Plan plan;
+  int sm_count = 148;
+};
+
+namespace {
+
+int fail(syl_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                        \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) return fail(h, SYL_E_CUDA, "%s: %s", #expr, cudaGetErrorString(_e));  \
+  } while (0)
+
+template <typename T>
+T* dev_alloc(syl_handle* h, size_t n) {
+  void* p = nullptr;
+  if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) return nullptr;
+  h->owned.push_back(p);
+  return reinterpret_cast<T*>(p);
+}
+
+const float* raw_ptr(syl_handle* h, const std::string& name, size_t expect_elems) {
+  auto it = h->raw.find(name);
+  if (it == h->raw.end()) {
+    fail(h, SYL_E_STATE, "missing weight '%s'", name.c_str());
+    return nullptr;
+  }
+  size_t n = 1;
+  for (int64_t d : it->second.second) n *= (size_t)d;
+  if (n != expect_elems) {
+    fail(h, SYL_E_STATE, "weight '%s' has %zu elements, expected %zu", name.c_str(), n, expect_elems);
+    return nullptr;
+  }
+  return it->second.first;
+}
+
+bool make_weight_maps(syl_handle* h, PackedLinear& w, int block_n) {
+  uint64_t dims[2] = {(uint64_t)w.K, (uint64_t)w.N};
+  uint64_t str[2] = {1, (uint64_t)w.K};
+  return make_tmap_f16(&w.map_hi, w.hi, 2, dims, str, block_n, &h->err) &&
+         make_tmap_f16(&w.map_lo, w.lo, 2, dims, str, block_n, &h->err);
+}
+
+// pack a torch Linear weight [N][K] (+ bias) ; several sources may be concatenated along N (QKV)
+int pack_linear(syl_handle* h, PackedLinear& out, const std::vector<std::string>& wnames,
+                const std::vector<std::string>& bnames, int n_each, int K) {
+  const int N = n_each * (int)wnames.size();
+  out.N = N;
+  out.K = K;
+  out.hi = dev_alloc<__half>(h, (size_t)N * K);
+  out.lo = dev_alloc<__half>(h, (size_t)N * K);
+  out.bias = dev_alloc<float>(h, N);
+  if (!out.hi || !out.lo || !out.bias) return fail(h, SYL_E_CUDA, "cudaMalloc failed while packing weights");
+  for (size_t i = 0; i < wnames.size(); ++i) {
+    const float* w = raw_ptr(h, wnames[i], (size_t)n_each * K);
+    const float* b = raw_ptr(h, bnames[i], (size_t)n_each);
+    if (!w || !b) return SYL_E_STATE;
+    const size_t n = (size_t)n_each * K;
+    split_f32_kernel<<<grid_for(n), 256>>>(w, out.hi + i * n, out.lo + i * n, n);
+    CUDA_TRY(h, cudaMemcpy(out.bias + i * n_each, b, n_each * sizeof(float), cudaMemcpyDeviceToDevice));
+  }
+  if (!make_weight_maps(h, out, 256)) return SYL_E_CUDA;
+  return SYL_OK;
+}
+
+float* copy_vec(syl_handle* h, const std::string& name, size_t n) {
+  const float* src = raw_ptr(h, name, n);
+  if (!src) return nullptr;
+  float* dst = dev_alloc<float>(h, n);
+  if (!dst) {
+    fail(h, SYL_E_CUDA, "cudaMalloc failed");
+    return nullptr;
+  }
+  if (cudaMemcpy(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice) != cudaSuccess) {
+    fail(h, SYL_E_CUDA, "cudaMemcpy failed for %s", name.c_str());
+    return nullptr;
+  }
+  return dst;
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace layout
+// ------------------------------------------------------------------------------------------------
+void conv_lengths(int t_samp, int* L) {
+  int n = t_samp;
+  for (int i = 0; i < 7; ++i) {
+    n = (n >= kConvK[i]) ? (n - kConvK[i]) / kConvS[i] + 1 : 0;
+    L[i] = n;
+  }
+}
+
+WsLayout make_layout(int batch, int t_samp) {
+  WsLayout w;
+  conv_lengths(t_samp, w.L);
+  w.T = w.L[6];
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 1023) & ~size_t(1023);
+    return o;
+  };
+  const size_t B = batch, M = B * w.T;
+  w.mom = take(B * C0_NMOM * sizeof(double));
+  w.gn_scale = take(B * kC * sizeof(float));
+  w.gn_shift = take(B * kC * sizeof(float));
+  w.valid = take(B * sizeof(int32_t));
+  w.nsq = take(M * sizeof(float));
+  w.seg_scratch = take(B * 6 * (size_t)(w.T + 1) * sizeof(int32_t));
+  for (int i = 0; i < 6; ++i) {
+    w.act_hi[i] = take(B * w.L[i] * kC * sizeof(__half));
+    w.act_lo[i] = take(B * w.L[i] * kC * sizeof(__half));
+  }
+  w.conv6 = take(M * kC * sizeof(float));
+  w.ln_hi = take(M * kC * sizeof(__half));
+  w.ln_lo = take(M * kC * sizeof(__half));
+  w.h = take(M * kH * sizeof(float));
+  w.h16_hi = take(M * kH * sizeof(__half));
+  w.h16_lo = take(M * kH * sizeof(__half));
+  w.pos = take(M * kH * sizeof(float));
+  w.pre = take(M * kH * sizeof(float));
+  w.qkv = take(M * 3 * kH * sizeof(__half));
+  w.ctx_hi = take(M * kH * sizeof(__half));
+  w.ctx_lo = take(M * kH * sizeof(__half));
+  w.mid_hi = take(M * kF * sizeof(__half));
+  w.mid_lo = take(M * kF * sizeof(__half));
+  w.total = off;
+  return w;
+}
+
+template <typename T>
+T* at(void* ws, size_t off) {
+  return reinterpret_cast<T*>(reinterpret_cast<uint8_t*>(ws) + off);
+}
+
+GemmParams base_params() {
+  GemmParams p;
+  memset(&p, 0, sizeof p);
+  p.n_pass = 1;
+  p.col_scale = 1.0f;
+  p.col_scale_limit = 0;
+  return p;
+}
+
+// plain [M,K] row-major A operand
+bool make_plain_a(syl_handle* h, GemmOp& op, const __half* hi, const __half* lo, int M, int K) {
+  uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, 1};
+  uint64_t str[3] = {1, (uint64_t)K, (uint64_t)M * K};
+  if (!make_tmap_f16(&op.a_hi, hi, 3, dims, str, 128, &h->err)) return false;
+  if (!make_tmap_f16(&op.a_lo, lo ? lo : hi, 3, dims, str, 128, &h->err)) return false;
+  op.p.rows_per_batch = M;
+  op.p.batches = 1;
+  op.p.kb_per_pass = K / GEMM_BLOCK_K;
+  op.p.kb_per_tap = K / GEMM_BLOCK_K;
+  op.p.tap_row_step = 0;
+  op.p.row_offset = 0;
+  op.p.a_col_per_ntile = 0;
+  return true;
+}
+
+int launch_gemm(syl_handle* h, const GemmOp& op, cudaStream_t st, int sm_count) {
+  const GemmParams& p = op.p;
+  const int tiles_m = p.batches * ((p.rows_per_batch + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M);
+  const int tiles = tiles_m * (p.N / op.block_n);
+  const int grid = std::min(tiles, sm_count);
+  if (grid <= 0) return SYL_OK;
+  if (op.block_n == 256) {
+    gemm_tc_kernel<256><<<grid, GEMM_THREADS, GemmSmem<256>::kTotal, st>>>(op.a_hi, op.a_lo, op.w->map_hi, op.w->map_lo, p);
+  } else if (op.block_n == 48) {
+    gemm_tc_kernel<48><<<grid, GEMM_THREADS, GemmSmem<48>::kTotal, st>>>(op.a_hi, op.a_lo, op.w->map_hi, op.w->map_lo, p);
+  } else {
+    return fail(h, SYL_E_ARG, "unsupported block_n %d", op.block_n);
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  return SYL_OK;
+}
+
+int set_kernel_attrs(syl_handle* h) {
+  CUDA_TRY(h, cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<256>::kTotal));
+  CUDA_TRY(h, cudaFuncSetAttribute(gemm_tc_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<48>::kTotal));
+  CUDA_TRY(h, cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
+  return SYL_OK;
+}
+
+bool g_attrs_set = false;
+int ensure_attrs(syl_handle* h) {
+  if (g_attrs_set) return SYL_OK;
+  int rc = set_kernel_attrs(h);
+  if (rc == SYL_OK) g_attrs_set = true;
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan: tensor maps + GEMM parameters for one (batch, t_samp, workspace, hidden) combination
+// ------------------------------------------------------------------------------------------------
+int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
+  Plan& pl = h->plan;
+  if (pl.valid && pl.batch == batch && pl.t_samp == t_samp && pl.ws == ws && pl.hidden == hidden) return SYL_OK;
+  pl.valid = false;
+  pl.batch = batch;
+  pl.t_samp = t_samp;
+  pl.ws = ws;
+  pl.hidden = hidden;
+  pl.lay = make_layout(batch, t_samp);
+  const WsLayout& L = pl.lay;
+  const int T = L.T, M = batch * T;
+  const bool split_conv = h->mode & SYL_SPLIT_CONV, split_proj = h->mode & SYL_SPLIT_PROJ,
+             split_enc = h->mode & SYL_SPLIT_ENC;
+
+  // conv1..conv6: A = overlapping-row view of the previous channels-last activation
+  for (int i = 1; i <= 6; ++i) {
+    GemmOp& op = pl.conv[i - 1];
+    op.p = base_params();
+    op.w = &h->convw[i - 1];
+    op.block_n = 256;
+    const int k = kConvK[i], s = kConvS[i], Lin = L.L[i - 1], Lout = L.L[i];
+    uint64_t dims[3] = {(uint64_t)k * kC, (uint64_t)Lout, (uint64_t)batch};
+    uint64_t str[3] = {1, (uint64_t)s * kC, (uint64_t)Lin * kC};
+    if (!make_tmap_f16(&op.a_hi, at<__half>(ws, L.act_hi[i - 1]), 3, dims, str, 128, &h->err)) return SYL_E_CUDA;
+    if (!make_tmap_f16(&op.a_lo, at<__half>(ws, L.act_lo[i - 1]), 3, dims, str, 128, &h->err)) return SYL_E_CUDA;
+    op.p.rows_per_batch = Lout;
+    op.p.batches = batch;
+    op.p.N = kC;
+    op.p.kb_per_pass = k * kC / GEMM_BLOCK_K;
+    op.p.kb_per_tap = op.p.kb_per_pass;
+    op.p.n_pass = split_conv ? 3 : 1;
+    op.p.act = 1;
+    op.p.ldo = kC;
+    if (i < 6) {
+      op.p.out_hi = at<__half>(ws, L.act_hi[i]);
+      op.p.out_lo = split_conv ? at<__half>(ws, L.act_lo[i]) : nullptr;
+    } else {
+      op.p.out_f32 = at<float>(ws, L.conv6);
+    }
+  }
+  // feature projection: LN(512) output -> 768, bias, zero padded frames (modeling_hubert.py:229, :429-432)
+  {
+    GemmOp& op = pl.proj;
+    op.p = base_params();
+    op.w = &h->proj;
+    op.block_n = 256;
+    if (!make_plain_a(h, op, at<__half>(ws, L.ln_hi), at<__half>(ws, L.ln_lo), M, kC)) return SYL_E_CUDA;
+    op.p.rows_per_batch = T;   // per-utterance tiles so that valid_rows indexes the batch
+    op.p.batches = batch;
+    {
+      uint64_t dims[3] = {(uint64_t)kC, (uint64_t)T, (uint64_t)batch};
+      uint64_t str[3] = {1, (uint64_t)kC, (uint64_t)T * kC};
+      if (!make_tmap_f16(&op.a_hi, at<__half>(ws, L.ln_hi), 3, dims, str, 128, &h->err)) return SYL_E_CUDA;
+      if (!make_tmap_f16(&op.a_lo, at<__half>(ws, L.ln_lo), 3, dims, str, 128, &h->err)) return SYL_E_CUDA;
+    }
+    op.p.N = kH;
+    op.p.n_pass = split_proj ? 3 : 1;
+    op.p.bias = h->proj.bias;
+    op.p.valid_rows = at<int32_t>(ws, L.valid);
+    op.p.out_f32 = at<float>(ws, L.h);
+    op.p.out_hi = at<__half>(ws, L.h16_hi);
+    op.p.out_lo = split_proj ? at<__half>(ws, L.h16_lo) : nullptr;
+    op.p.ldo = kH;
+  }
+  // positional conv: 16 groups x (48 -> 48), 128 taps; K loop over taps, A rows shift by one frame per tap
+  {
+    GemmOp& op = pl.pos;
+    op.p = base_params();
+    op.w = &h->pos;
+    op.block_n = 48;
+    uint64_t dims[3] = {(uint64_t)kH, (uint64_t)T, (uint64_t)batch};
+    uint64_t str[3] = {1, (uint64_t)kH, (uint64_t)T * kH};
+    if (!make_tmap_f16(&op.a_hi, at<__half>(ws, L.h16_hi), 3, dims, str, 128, &h->err)) return SYL_E_CUDA;
+    if (!make_tmap_f16(&op.a_lo, at<__half>(ws, L.h16_lo), 3, dims, str, 128, &h->err)) return SYL_E_CUDA;
+    op.p.rows_per_batch = T;
+    op.p.batches = batch;
+    op.p.N = kH;
+    op.p.kb_per_pass = kPosK;
+    op.p.kb_per_tap = 1;
+    op.p.tap_row_step = 1;
+    op.p.row_offset = -(kPosK / 2);
+    op.p.a_col_per_ntile = kPosCg;
+    op.p.n_pass = split_proj ? 3 : 1;
+    op.p.bias = h->pos.bias;
+    op.p.act = 1;
+    op.p.out_f32 = at<float>(ws, L.pos);
+    op.p.ldo = kH;
+  }
+  // encoder layers
+  const int nl = h->n_layers;
+  pl.qkv.assign(nl, GemmOp());
+  pl.out.assign(nl, GemmOp());
+  pl.ffn1.assign(nl, GemmOp());
+  pl.ffn2.assign(nl, GemmOp());
+  for (int l = 0; l < nl; ++l) {
+    const LayerW& w = h->layers[l];
+    {
+      GemmOp& op = pl.qkv[l];
+      op.p = base_params();
+      op.w = &w.qkv;
+      if (!make_plain_a(h, op, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), M, kH)) return SYL_E_CUDA;
+      op.p.N = 3 * kH;
+      op.p.n_pass = split_enc ? 3 : 1;
+      op.p.bias = w.qkv.bias;
+      op.p.col_scale = 0.125f;        // head_dim ** -0.5, exact (modeling_hubert.py:287)
+      op.p.col_scale_limit = kH;
+      op.p.out_hi = at<__half>(ws, L.qkv);
+      op.p.ldo = 3 * kH;
+    }
+    {
+      GemmOp& op = pl.out[l];
+      op.p = base_params();
+      op.w = &w.out;
+      if (!make_plain_a(h, op, at<__half>(ws, L.ctx_hi), at<__half>(ws, L.ctx_lo), M, kH)) return SYL_E_CUDA;
+      op.p.N = kH;
+      op.p.n_pass = split_enc ? 3 : 1;
+      op.p.bias = w.out.bias;
+      op.p.residual = at<float>(ws, L.h);
+      op.p.out_f32 = at<float>(ws, L.pre);
+      op.p.ldo = kH;
+    }
+    {
+      GemmOp& op = pl.ffn1[l];
+      op.p = base_params();
+      op.w = &w.ffn1;
+      if (!make_plain_a(h, op, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), M, kH)) return SYL_E_CUDA;
+      op.p.N = kF;
+      op.p.n_pass = split_enc ? 3 : 1;
+      op.p.bias = w.ffn1.bias;
+      op.p.act = 1;
+      op.p.out_hi = at<__half>(ws, L.mid_hi);
+      op.p.out_lo = split_enc ? at<__half>(ws, L.mid_lo) : nullptr;
+      op.p.ldo = kF;
+    }
+    {
+      GemmOp& op = pl.ffn2[l];
+      op.p = base_params();
+      op.w = &w.ffn2;
+      if (!make_plain_a(h, op, at<__half>(ws, L.mid_hi), at<__half>(ws, L.mid_lo), M, kF)) return SYL_E_CUDA;
+      op.p.N = kH;
+      op.p.n_pass = split_enc ? 3 : 1;
+      op.p.bias = w.ffn2.bias;
+      op.p.residual = at<float>(ws, L.h);
+      op.p.out_f32 = at<float>(ws, L.pre);
+      op.p.ldo = kH;
+    }
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)3 * kH, (uint64_t)T, (uint64_t)batch};
+    uint64_t str[3] = {1, (uint64_t)3 * kH, (uint64_t)T * 3 * kH};
+    if (!make_tmap_f16(&pl.attn_map, at<__half>(ws, L.qkv), 3, dims, str, 128, &h->err)) return SYL_E_CUDA;
+  }
+  pl.valid = true;
+  return SYL_OK;
+}
+
+template <int D>
+void launch_ln(const float* x, const float* add, const float* g, const float* b, int rows, float* of, __half* ohi,
+               __half* olo, cudaStream_t st) {
+  const int warps = 8;
+  layernorm_rows_kernel<D><<<(rows + warps - 1) / warps, warps * 32, 0, st>>>(x, add, g, b, rows, of, ohi, olo);
+}
+
+int run_frontend(syl_handle* h, const float* wav, cudaStream_t st) {
+  Plan& pl = h->plan;
+  const WsLayout& L = pl.lay;
+  void* ws = pl.ws;
+  const int B = pl.batch, L0 = L.L[0];
+  CUDA_TRY(h, cudaMemsetAsync(at<double>(ws, L.mom), 0, (size_t)B * C0_NMOM * sizeof(double), st));
+  conv0_moments_kernel<<<dim3((L0 + MOM_T_PER_BLOCK - 1) / MOM_T_PER_BLOCK, B), MOM_THREADS, 0, st>>>(
+      wav, pl.t_samp, L0, at<double>(ws, L.mom));
+  conv0_gn_coeff_kernel<<<B, kC, 0, st>>>(at<double>(ws, L.mom), h->conv0_w, h->gn_g, h->gn_b, L0,
+                                          at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift));
+  conv0_apply_kernel<<<dim3((L0 + C0A_T - 1) / C0A_T, B), C0A_THREADS, 0, st>>>(
+      wav, pl.t_samp, L0, h->conv0_w, at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift),
+      at<__half>(ws, L.act_hi[0]), (h->mode & SYL_SPLIT_CONV) ? at<__half>(ws, L.act_lo[0]) : nullptr);
+  CUDA_TRY(h, cudaGetLastError());
+  for (int i = 0; i < 6; ++i) {
+    int rc = launch_gemm(h, pl.conv[i], st, h->sm_count);
+    if (rc) return rc;
+  }
+  return SYL_OK;
+}
+
+int run_layer(syl_handle* h, int l, float* h_out, cudaStream_t st) {
+  Plan& pl = h->plan;
+  const WsLayout& L = pl.lay;
+  void* ws = pl.ws;
+  const int B = pl.batch, T = L.T, M = B * T;
+  const LayerW& w = h->layers[l];
+  const bool split_enc = h->mode & SYL_SPLIT_ENC;
+  int rc;
+  if ((rc = launch_gemm(h, pl.qkv[l], st, h->sm_count))) return rc;
+  AttnParams ap;
+  ap.T = T;
+  ap.heads = kHeads;
+  ap.model_dim = kH;
+  ap.kv_len = at<int32_t>(ws, L.valid);
+  ap.out_hi = at<__half>(ws, L.ctx_hi);
+  ap.out_lo = split_enc ? at<__half>(ws, L.ctx_lo) : nullptr;
+  attention_kernel<<<dim3((T + ATT_BQ - 1) / ATT_BQ, kHeads, B), ATT_THREADS, ATT_SMEM_TOTAL, st>>>(pl.attn_map, ap);
+  CUDA_TRY(h, cudaGetLastError());
+  if ((rc = launch_gemm(h, pl.out[l], st, h->sm_count))) return rc;
+  launch_ln<kH>(at<float>(ws, L.pre), nullptr, w.ln1_g, w.ln1_b, M, at<float>(ws, L.h), at<__half>(ws, L.h16_hi),
+                split_enc ? at<__half>(ws, L.h16_lo) : nullptr, st);
+  if ((rc = launch_gemm(h, pl.ffn1[l], st, h->sm_count))) return rc;
+  if ((rc = launch_gemm(h, pl.ffn2[l], st, h->sm_count))) return rc;
+  launch_ln<kH>(at<float>(ws, L.pre), nullptr, w.ln2_g, w.ln2_b, M, h_out, at<__half>(ws, L.h16_hi),
+                split_enc ? at<__half>(ws, L.h16_lo) : nullptr, st);
+  CUDA_TRY(h, cudaGetLastError());
+  return SYL_OK;
+}
+
+int run_segment(const float* states, int B, int T, float thr_norm, float thr_merge, int32_t* seg, int32_t* seg_count,
+                float* seg_feat, int max_seg, float* nsq, int32_t* scratch, cudaStream_t st) {
+  const int rows = B * T;
+  frame_sqnorm_kernel<<<(rows + 7) / 8, 256, 0, st>>>(states, rows, nsq);
+  segment_kernel<<<B, 32, 0, st>>>(states, nsq, T, thr_norm, thr_merge, seg, seg_count, max_seg, scratch);
+  if (seg_feat) segment_pool_kernel<<<dim3(max_seg, B), 192, 0, st>>>(states, T, seg, seg_count, max_seg, seg_feat);
+  return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
+}
+
+}  // namespace
+
+// ================================================================================================
+// exported C ABI
+// ================================================================================================
+extern "C" {
+
+const char* syl_last_error(const syl_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int syl_num_frames(int n_samples) {
+  int L[7];
+  conv_lengths(n_samples, L);
+  return L[6];
+}
+
+int syl_create(syl_handle** out, int device, int n_layers, int mode) {
+  if (!out || n_layers < 1 || n_layers > 48) return fail(nullptr, SYL_E_ARG, "syl_create: bad arguments");
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
+    return fail(nullptr, SYL_E_CUDA, "syl_create: CUDA device %d not available (%d devices); there is no CPU fallback",
+                device, count);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, SYL_E_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10)
+    return fail(nullptr, SYL_E_CUDA, "syl_create: device %d is sm_%d%d; this library contains sm_100a code only", device,
+                prop.major, prop.minor);
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, SYL_E_CUDA, "cudaSetDevice failed");
+  syl_handle* h = new syl_handle();
+  h->device = device;
+  h->n_layers = n_layers;
+  h->mode = mode;
+  h->sm_count = prop.multiProcessorCount;
+  *out = h;
+  return SYL_OK;
+}
+
+void syl_destroy(syl_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (auto& kv : h->raw) cudaFree(kv.second.first);
+  for (void* p : h->owned) cudaFree(p);
+  delete h;
+}
+
+int syl_load_weight(syl_handle* h, const char* name, const void* dev_ptr, const int64_t* shape, int ndim, int dtype) {
+  if (!h || !name || !dev_ptr || !shape || ndim < 1 || ndim > 4) return fail(h, SYL_E_ARG, "syl_load_weight: bad arguments");
+  if (dtype != SYL_DTYPE_F32) return fail(h, SYL_E_ARG, "syl_load_weight: only fp32 tensors are accepted");
+  if (h->finalized) return fail(h, SYL_E_STATE, "syl_load_weight after syl_finalize");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  size_t n = 1;
+  std::vector<int64_t> shp(shape, shape + ndim);
+  for (int64_t d : shp) n *= (size_t)d;
+  std::string key(name);
+  // legacy weight-norm naming
+  const std::string pre = "encoder.pos_conv_embed.conv.";
+  if (key == pre + "weight_g") key = pre + "parametrizations.weight.original0";
+  if (key == pre + "weight_v") key = pre + "parametrizations.weight.original1";
+  float* p = nullptr;
+  CUDA_TRY(h, cudaMalloc(&p, n * sizeof(float)));
+  CUDA_TRY(h, cudaMemcpy(p, dev_ptr, n * sizeof(float), cudaMemcpyDeviceToDevice));
+  auto it = h->raw.find(key);
+  if (it != h->raw.end()) cudaFree(it->second.first);
+  h->raw[key] = std::make_pair(p, shp);
+  return SYL_OK;
+}
+
+int syl_finalize(syl_handle* h) {
+  if (!h) return SYL_E_ARG;
+  if (h->finalized) return SYL_OK;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  int rc = ensure_attrs(h);
+  if (rc) return rc;
+  const std::string fe = "feature_extractor.conv_layers.";
+  if (!(h->conv0_w = copy_vec(h, fe + "0.conv.weight", (size_t)kC * 10))) return SYL_E_STATE;
+  if (!(h->gn_g = copy_vec(h, fe + "0.layer_norm.weight", kC))) return SYL_E_STATE;
+  if (!(h->gn_b = copy_vec(h, fe + "0.layer_norm.bias", kC))) return SYL_E_STATE;
+  for (int i = 1; i <= 6; ++i) {
+    const int k = kConvK[i];
+    const float* w = raw_ptr(h, fe + std::to_string(i) + ".conv.weight", (size_t)kC * kC * k);
+    if (!w) return SYL_E_STATE;
+    PackedLinear& pw = h->convw[i - 1];
+    pw.N = kC;
+    pw.K = k * kC;
+    pw.hi = dev_alloc<__half>(h, (size_t)kC * kC * k);
+    pw.lo = dev_alloc<__half>(h, (size_t)kC * kC * k);
+    if (!pw.hi || !pw.lo) return fail(h, SYL_E_CUDA, "cudaMalloc failed");
+    pack_conv_w_kernel<<<grid_for((size_t)kC * kC * k), 256>>>(w, k, pw.hi, pw.lo);
+    if (!make_weight_maps(h, pw, 256)) return SYL_E_CUDA;
+  }
+  if (!(h->fp_ln_g = copy_vec(h, "feature_projection.layer_norm.weight", kC))) return SYL_E_STATE;
+  if (!(h->fp_ln_b = copy_vec(h, "feature_projection.layer_norm.bias", kC))) return SYL_E_STATE;
+  if ((rc = pack_linear(h, h->proj, {"feature_projection.projection.weight"}, {"feature_projection.projection.bias"}, kH, kC)))
+    return rc;
+  {
+    const std::string pc = "encoder.pos_conv_embed.conv.";
+    const float* g = raw_ptr(h, pc + "parametrizations.weight.original0", kPosK);
+    const float* v = raw_ptr(h, pc + "parametrizations.weight.original1", (size_t)kH * kPosCg * kPosK);
+    if (!g || !v) return SYL_E_STATE;
+    float* norm = dev_alloc<float>(h, kPosK);
+    PackedLinear& pw = h->pos;
+    pw.N = kH;
+    pw.K = kPosK * 64;
+    pw.hi = dev_alloc<__half>(h, (size_t)kH * kPosK * 64);
+    pw.lo = dev_alloc<__half>(h, (size_t)kH * kPosK * 64);
+    if (!norm || !pw.hi || !pw.lo) return fail(h, SYL_E_CUDA, "cudaMalloc failed");
+    if (!(pw.bias = copy_vec(h, pc + "bias", kH))) return SYL_E_STATE;
+    pos_tap_norm_kernel<<<kPosK, 256>>>(v, norm);
+    pack_pos_w_kernel<<<grid_for((size_t)kH * kPosK * 64), 256>>>(v, g, norm, pw.hi, pw.lo);
+    if (!make_weight_maps(h, pw, 48)) return SYL_E_CUDA;
+  }
+  if (!(h->enc_ln_g = copy_vec(h, "encoder.layer_norm.weight", kH))) return SYL_E_STATE;
+  if (!(h->enc_ln_b = copy_vec(h, "encoder.layer_norm.bias", kH))) return SYL_E_STATE;
+  h->layers.resize(h->n_layers);
+  for (int l = 0; l < h->n_layers; ++l) {
+    const std::string p = "encoder.layers." + std::to_string(l) + ".";
+    LayerW& w = h->layers[l];
+    if ((rc = pack_linear(h, w.qkv, {p + "attention.q_proj.weight", p + "attention.k_proj.weight", p + "attention.v_proj.weight"},
+                          {p + "attention.q_proj.bias", p + "attention.k_proj.bias", p + "attention.v_proj.bias"}, kH, kH)))
+      return rc;
+    if ((rc = pack_linear(h, w.out, {p + "attention.out_proj.weight"}, {p + "attention.out_proj.bias"}, kH, kH))) return rc;
+    if ((rc = pack_linear(h, w.ffn1, {p + "feed_forward.intermediate_dense.weight"}, {p + "feed_forward.intermediate_dense.bias"}, kF, kH)))
+      return rc;
+    if ((rc = pack_linear(h, w.ffn2, {p + "feed_forward.output_dense.weight"}, {p + "feed_forward.output_dense.bias"}, kH, kF)))
+      return rc;
+    if (!(w.ln1_g = copy_vec(h, p + "layer_norm.weight", kH))) return SYL_E_STATE;
+    if (!(w.ln1_b = copy_vec(h, p + "layer_norm.bias", kH))) return SYL_E_STATE;
+    if (!(w.ln2_g = copy_vec(h, p + "final_layer_norm.weight", kH))) return SYL_E_STATE;
+    if (!(w.ln2_b = copy_vec(h, p + "final_layer_norm.bias", kH))) return SYL_E_STATE;
+  }
+  CUDA_TRY(h, cudaDeviceSynchronize());
+  CUDA_TRY(h, cudaGetLastError());
+  for (auto& kv : h->raw) cudaFree(kv.second.first);
+  h->raw.clear();
+  h->finalized = true;
+  return SYL_OK;
+}
+
+size_t syl_workspace_bytes(const syl_handle* h, int batch, int t_samp_max) {
+  (void)h;
+  if (batch <= 0 || t_samp_max < 400) return 0;
+  return make_layout(batch, t_samp_max).total;
+}
+
+int syl_set_active_layers(syl_handle* h, int n) {
+  if (!h) return SYL_E_ARG;
+  h->active_layers = n;
+  return SYL_OK;
+}
+
+int syl_forward_launch_count(const syl_handle* h, int with_segmentation) {
+  if (!h) return 0;
+  const int nl = (h->active_layers >= 0 && h->active_layers < h->n_layers) ? h->active_layers : h->n_layers;
+  // valid_frames, moments, gn_coeff, conv0_apply, 6 conv GEMMs, LN512, proj, pos, LN ; per layer 4 GEMM + attn + 2 LN
+  return 4 + 6 + 4 + nl * 7 + (with_segmentation ? 3 : 0);
+}
+
+int syl_forward(syl_handle* h, const float* wav, const int32_t* n_samples, int batch, int t_samp_max, float* hidden,
+                int32_t* seg, int32_t* seg_count, float* seg_feat, int max_seg, float thr_norm, float thr_merge,
+                void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return SYL_E_ARG;
+  if (!h->finalized) return fail(h, SYL_E_STATE, "syl_forward before syl_finalize");
+  if (!wav || !hidden || !workspace || batch <= 0) return fail(h, SYL_E_ARG, "syl_forward: null pointer or empty batch");
+  if (t_samp_max < 400) return fail(h, SYL_E_ARG, "syl_forward: need at least 400 samples (one frame), got %d", t_samp_max);
+  const size_t need = syl_workspace_bytes(h, batch, t_samp_max);
+  if (workspace_bytes < need) return fail(h, SYL_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
+  if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return fail(h, SYL_E_ARG, "workspace must be 1024-byte aligned");
+  if (seg && (!seg_count || max_seg <= 0)) return fail(h, SYL_E_ARG, "syl_forward: seg needs seg_count and max_seg > 0");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = build_plan(h, batch, t_samp_max, workspace, hidden);
+  if (rc) return rc;
+  Plan& pl = h->plan;
+  const WsLayout& L = pl.lay;
+  const int T = L.T, M = batch * T;
+  const bool split_proj = h->mode & SYL_SPLIT_PROJ, split_enc = h->mode & SYL_SPLIT_ENC;
+
+  if (n_samples)
+    valid_frames_kernel<<<(batch + 127) / 128, 128, 0, st>>>(n_samples, batch, T, at<int32_t>(workspace, L.valid));
+  else
+    fill_i32_kernel<<<(batch + 127) / 128, 128, 0, st>>>(at<int32_t>(workspace, L.valid), batch, T);
+  if ((rc = run_frontend(h, wav, st))) return rc;
+  launch_ln<kC>(at<float>(workspace, L.conv6), nullptr, h->fp_ln_g, h->fp_ln_b, M, nullptr, at<__half>(workspace, L.ln_hi),
+                split_proj ? at<__half>(workspace, L.ln_lo) : nullptr, st);
+  if ((rc = launch_gemm(h, pl.proj, st, h->sm_count))) return rc;
+  if ((rc = launch_gemm(h, pl.pos, st, h->sm_count))) return rc;
+  const int nl = (h->active_layers >= 0 && h->active_layers < h->n_layers) ? h->active_layers : h->n_layers;
+  // h = LN(h + pos)   (modeling_hubert.py:441-442); with zero layers this is already the output
+  launch_ln<kH>(at<float>(workspace, L.h), at<float>(workspace, L.pos), h->enc_ln_g, h->enc_ln_b, M,
+                nl == 0 ? hidden : at<float>(workspace, L.h), at<__half>(workspace, L.h16_hi),
+                split_enc ? at<__half>(workspace, L.h16_lo) : nullptr, st);
+  CUDA_TRY(h, cudaGetLastError());
+  for (int l = 0; l < nl; ++l) {
+    float* out = (l == nl - 1) ? hidden : at<float>(workspace, L.h);
+    // the residual for FFN2 must be the post-attention LN output, which run_layer keeps in workspace h
+    if ((rc = run_layer(h, l, out, st))) return rc;
+  }
+  if (seg) {
+    rc = run_segment(hidden, batch, T, thr_norm, thr_merge, seg, seg_count, seg_feat, max_seg,
+                     at<float>(workspace, L.nsq), at<int32_t>(workspace, L.seg_scratch), st);
+    if (rc) return fail(h, rc, "segmentation launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  return SYL_OK;
+}
+
+int syl_conv_frontend(syl_handle* h, const float* wav, int batch, int t_samp_max, float* feats, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  if (!h) return SYL_E_ARG;
+  if (!h->finalized) return fail(h, SYL_E_STATE, "syl_conv_frontend before syl_finalize");
+  if (!wav || !feats || !workspace || batch <= 0 || t_samp_max < 400) return fail(h, SYL_E_ARG, "syl_conv_frontend: bad arguments");
+  const size_t need = syl_workspace_bytes(h, batch, t_samp_max);
+  if (workspace_bytes < need) return fail(h, SYL_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = build_plan(h, batch, t_samp_max, workspace, nullptr);
+  if (rc) return rc;
+  if ((rc = run_frontend(h, wav, st))) return rc;
+  const WsLayout& L = h->plan.lay;
+  CUDA_TRY(h, cudaMemcpyAsync(feats, at<float>(workspace, L.conv6), (size_t)batch * L.T * kC * sizeof(float),
+                              cudaMemcpyDeviceToDevice, st));
+  return SYL_OK;
+}
+
+int syl_encoder_layer(syl_handle* h, int layer, const float* h_in, const int32_t* valid_frames, int batch, int T,
+                      float* h_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return SYL_E_ARG;
+  if (!h->finalized) return fail(h, SYL_E_STATE, "syl_encoder_layer before syl_finalize");
+  if (!h_in || !h_out || !workspace || batch <= 0 || T <= 0 || layer < 0 || layer >= h->n_layers)
+    return fail(h, SYL_E_ARG, "syl_encoder_layer: bad arguments");
+  // smallest sample count that yields exactly T frames
+  int n = T;
+  for (int i = 6; i >= 0; --i) n = (n - 1) * kConvS[i] + kConvK[i];
+  const size_t need = syl_workspace_bytes(h, batch, n);
+  if (workspace_bytes < need) return fail(h, SYL_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = build_plan(h, batch, n, workspace, nullptr);
+  if (rc) return rc;
+  const WsLayout& L = h->plan.lay;
+  const size_t M = (size_t)batch * T;
+  if (valid_frames)
+    CUDA_TRY(h, cudaMemcpyAsync(at<int32_t>(workspace, L.valid), valid_frames, batch * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  else
+    fill_i32_kernel<<<(batch + 127) / 128, 128, 0, st>>>(at<int32_t>(workspace, L.valid), batch, T);
+  CUDA_TRY(h, cudaMemcpyAsync(at<float>(workspace, L.h), h_in, M * kH * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  split_f32_kernel<<<grid_for(M * kH), 256, 0, st>>>(h_in, at<__half>(workspace, L.h16_hi), at<__half>(workspace, L.h16_lo), M * kH);
+  return run_layer(h, layer, h_out, st);
+}
+
+int syl_attention(const void* qkv_f16, const int32_t* kv_len, int batch, int T, void* out_f16, void* stream) {
+  static std::string err;
+  if (!qkv_f16 || !out_f16 || batch <= 0 || T <= 0) return SYL_E_ARG;
+  if (cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL) != cudaSuccess)
+    return SYL_E_CUDA;
+  CUtensorMap map;
+  uint64_t dims[3] = {(uint64_t)3 * kH, (uint64_t)T, (uint64_t)batch};
+  uint64_t str[3] = {1, (uint64_t)3 * kH, (uint64_t)T * 3 * kH};
+  if (!make_tmap_f16(&map, qkv_f16, 3, dims, str, 128, &err)) {
+    g_create_error = err;
+    return SYL_E_CUDA;
+  }
+  AttnParams ap;
+  ap.T = T;
+  ap.heads = kHeads;
+  ap.model_dim = kH;
+  ap.kv_len = kv_len;
+  ap.out_hi = reinterpret_cast<__half*>(out_f16);
+  ap.out_lo = nullptr;
+  attention_kernel<<<dim3((T + ATT_BQ - 1) / ATT_BQ, kHeads, batch), ATT_THREADS, ATT_SMEM_TOTAL,
+                     reinterpret_cast<cudaStream_t>(stream)>>>(map, ap);
+  return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
+}
+
+size_t syl_segment_workspace_bytes(int batch, int T) {
+  if (batch <= 0 || T <= 0) return 0;
+  return (((size_t)batch * T * sizeof(float) + 1023) & ~size_t(1023)) + (size_t)batch * 6 * (T + 1) * sizeof(int32_t);
+}
+
+int syl_segment(const float* states, int batch, int T, float thr_norm, float thr_merge, int32_t* seg,
+                int32_t* seg_count, float* seg_feat, int max_seg, void* workspace, size_t workspace_bytes,
+                void* stream) {
+  if (!states || !seg || !seg_count || !workspace || batch <= 0 || T <= 0 || max_seg <= 0) return SYL_E_ARG;
+  if (workspace_bytes < syl_segment_workspace_bytes(batch, T)) return SYL_E_WORKSPACE;
+  float* nsq = reinterpret_cast<float*>(workspace);
+  int32_t* scratch = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(workspace) +
+                                                (((size_t)batch * T * sizeof(float) + 1023) & ~size_t(1023)));
+  return run_segment(states, batch, T, thr_norm, thr_merge, seg, seg_count, seg_feat, max_seg, nsq, scratch,
+                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t syl_gemm_workspace_bytes(int M, int N, int K) {
+  auto al = [](size_t b) { return (b + 1023) & ~size_t(1023); };
+  return 2 * al((size_t)M * K * 2) + 2 * al((size_t)N * K * 2);
+}
+
+int syl_gemm_f32(const float* A, const float* W, const float* bias, const float* residual, float* out, int M, int N,
+                 int K, int n_pass, int act, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!A || !W || !out || !workspace || M <= 0 || N <= 0 || K <= 0) return fail(nullptr, SYL_E_ARG, "syl_gemm_f32: bad arguments");
+  if (N % 256 != 0 || K % 64 != 0) return fail(nullptr, SYL_E_ARG, "syl_gemm_f32: N must be a multiple of 256 and K of 64");
+  if (n_pass != 1 && n_pass != 3) return fail(nullptr, SYL_E_ARG, "syl_gemm_f32: n_pass must be 1 or 3");
+  if (workspace_bytes < syl_gemm_workspace_bytes(M, N, K)) return fail(nullptr, SYL_E_WORKSPACE, "syl_gemm_f32: workspace too small");
+  if (cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<256>::kTotal) != cudaSuccess)
+    return fail(nullptr, SYL_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  auto al = [](size_t b) { return (b + 1023) & ~size_t(1023); };
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  __half* a_hi = reinterpret_cast<__half*>(ws);
+  __half* a_lo = reinterpret_cast<__half*>(ws + al((size_t)M * K * 2));
+  __half* w_hi = reinterpret_cast<__half*>(ws + 2 * al((size_t)M * K * 2));
+  __half* w_lo = reinterpret_cast<__half*>(ws + 2 * al((size_t)M * K * 2) + al((size_t)N * K * 2));
+  split_f32_kernel<<<grid_for((size_t)M * K), 256, 0, st>>>(A, a_hi, a_lo, (size_t)M * K);
+  split_f32_kernel<<<grid_for((size_t)N * K), 256, 0, st>>>(W, w_hi, w_lo, (size_t)N * K);
+  std::string err;
+  PackedLinear pw;
+  pw.hi = w_hi;
+  pw.lo = w_lo;
+  pw.N = N;
+  pw.K = K;
+  uint64_t wd[2] = {(uint64_t)K, (uint64_t)N}, wsd[2] = {1, (uint64_t)K};
+  if (!make_tmap_f16(&pw.map_hi, w_hi, 2, wd, wsd, 256, &err) || !make_tmap_f16(&pw.map_lo, w_lo, 2, wd, wsd, 256, &err))
+    return fail(nullptr, SYL_E_CUDA, "%s", err.c_str());
+  GemmOp op;
+  op.p = base_params();
+  op.w = &pw;
+  op.block_n = 256;
+  uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, 1}, str[3] = {1, (uint64_t)K, (uint64_t)M * K};
+  if (!make_tmap_f16(&op.a_hi, a_hi, 3, dims, str, 128, &err) || !make_tmap_f16(&op.a_lo, a_lo, 3, dims, str, 128, &err))
+    return fail(nullptr, SYL_E_CUDA, "%s", err.c_str());
+  op.p.rows_per_batch = M;
+  op.p.batches = 1;
+  op.p.N = N;
+  op.p.kb_per_pass = K / GEMM_BLOCK_K;
+  op.p.kb_per_tap = op.p.kb_per_pass;
+  op.p.n_pass = n_pass;
+  op.p.bias = bias;
+  op.p.residual = residual;
+  op.p.act = act;
+  op.p.out_f32 = out;
+  op.p.ldo = N;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = ((M + 127) / 128) * (N / 256);
+  gemm_tc_kernel<256><<<std::min(tiles, sms), GEMM_THREADS, GemmSmem<256>::kTotal, st>>>(op.a_hi, op.a_lo, pw.map_hi, pw.map_lo, op.p);
+  if (cudaGetLastError() != cudaSuccess) return fail(nullptr, SYL_E_CUDA, "gemm launch failed");
+  return SYL_OK;
+}
+
+int syl_powf_half(const float* x, float* y, int64_t n, void* stream) {
+  if (!x || !y || n <= 0) return SYL_E_ARG;
+  powf_half_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, n);
+  return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
+}
+
+int syl_read_stage(syl_handle* h, const char* name, float* out, size_t n_floats, void* stream) {
+  if (!h || !name || !out) return SYL_E_ARG;
+  if (!h->plan.valid) return fail(h, SYL_E_STATE, "syl_read_stage: no forward has run yet");
+  const Plan& pl = h->plan;
+  const WsLayout& L = pl.lay;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const std::string s(name);
+  const size_t B = pl.batch, M = B * L.T;
+  if (s.size() == 5 && s.compare(0, 4, "conv") == 0 && s[4] >= '0' && s[4] <= '5') {
+    const int i = s[4] - '0';
+    const size_t n = B * L.L[i] * kC;
+    if (n_floats < n) return fail(h, SYL_E_ARG, "syl_read_stage: output too small (%zu < %zu)", n_floats, n);
+    join_f16_kernel<<<grid_for(n), 256, 0, st>>>(at<__half>(pl.ws, L.act_hi[i]),
+                                                 (h->mode & SYL_SPLIT_CONV) ? at<__half>(pl.ws, L.act_lo[i]) : nullptr, out, n);
+    return SYL_OK;
+  }
+  const float* src = nullptr;
+  size_t n = 0;
+  if (s == "conv6") { src = at<float>(pl.ws, L.conv6); n = M * kC; }
+  else if (s == "pos") { src = at<float>(pl.ws, L.pos); n = M * kH; }
+  else if (s == "pre") { src = at<float>(pl.ws, L.pre); n = M * kH; }
+  else if (s == "h") { src = at<float>(pl.ws, L.h); n = M * kH; }
+  else return fail(h, SYL_E_ARG, "syl_read_stage: unknown stage '%s'", name);
+  if (n_floats < n) return fail(h, SYL_E_ARG, "syl_read_stage: output too small (%zu < %zu)", n_floats, n);
+  CUDA_TRY(h, cudaMemcpyAsync(out, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return SYL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,213 @@
+// Waveform front end: conv0 (1->512, k=10, s=5, no bias) + GroupNorm(512 groups) + erf-GELU, and the
+// row-wise LayerNorm kernels.  Reference arithmetic: transformers HubertGroupNormConvLayer
+// (modeling_hubert.py:154-175), HubertFeatureProjection (:225-231), HubertEncoder (:441-443),
+// HubertEncoderLayer (:394-398); reached from sylber/model/sylber.py:122.
+//
+// These stages are HBM bound.  The GroupNorm statistics never touch the 2 GB conv0 activation: because
+// conv0 is linear in the 10 taps, the per-channel sum and sum of squares over time follow from the
+// 10x10 second-moment matrix of the strided waveform windows,
+//     sum_t y_c[t]   = w_c . S          S[j]    = sum_t x[5t+j]
+//     sum_t y_c[t]^2 = w_c^T R w_c      R[j,j'] = sum_t x[5t+j] x[5t+j']
+// accumulated in fp64 (exact products of fp32 inputs), so the statistics pass reads only the waveform.
+#pragma once
+
+#include "common.cuh"
+
+namespace syl {
+
+constexpr int C0_K = 10;
+constexpr int C0_S = 5;
+constexpr int C0_OUT = 512;
+constexpr int C0_NMOM = C0_K + C0_K * (C0_K + 1) / 2;  // 10 sums + 55 upper-triangle second moments
+
+// ----------------------------------------------------------------------------------------------
+// conv0 moments: grid (chunks, B), block 128.  mom[b][65] must be zeroed before the launch.
+// ----------------------------------------------------------------------------------------------
+constexpr int MOM_THREADS = 128;
+constexpr int MOM_T_PER_BLOCK = 1024;
+
+__global__ void __launch_bounds__(MOM_THREADS)
+conv0_moments_kernel(const float* __restrict__ wav, int t_samp, int L0, double* __restrict__ mom) {
+  __shared__ float xs[MOM_T_PER_BLOCK * C0_S + C0_K];
+  __shared__ double red[C0_NMOM];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * MOM_T_PER_BLOCK;
+  const int nt = min(MOM_T_PER_BLOCK, L0 - t0);
+  const float* w = wav + (size_t)b * t_samp + (size_t)t0 * C0_S;
+  const int nsamp = nt * C0_S + (C0_K - C0_S);
+  for (int i = threadIdx.x; i < nsamp; i += MOM_THREADS) xs[i] = w[i];
+  if (threadIdx.x < C0_NMOM) red[threadIdx.x] = 0.0;
+  __syncthreads();
+
+  double acc[C0_NMOM];
+#pragma unroll
+  for (int i = 0; i < C0_NMOM; ++i) acc[i] = 0.0;
+  for (int t = threadIdx.x; t < nt; t += MOM_THREADS) {
+    double x[C0_K];
+#pragma unroll
+    for (int j = 0; j < C0_K; ++j) x[j] = (double)xs[t * C0_S + j];
+    int idx = C0_K;
+#pragma unroll
+    for (int j = 0; j < C0_K; ++j) {
+      acc[j] += x[j];
+#pragma unroll
+      for (int k = j; k < C0_K; ++k) acc[idx++] += x[j] * x[k];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < C0_NMOM; ++i) {
+    double v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane_id() == 0) atomicAdd(&red[i], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < C0_NMOM) atomicAdd(&mom[(size_t)b * C0_NMOM + threadIdx.x], red[threadIdx.x]);
+}
+
+// per (b, c): GroupNorm scale/shift so that  gn(y) = y * scale + shift   (eps 1e-5, biased variance)
+__global__ void conv0_gn_coeff_kernel(const double* __restrict__ mom, const float* __restrict__ w0,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta, int L0,
+                                      float* __restrict__ scale, float* __restrict__ shift) {
+  const int b = blockIdx.x;
+  const int c = threadIdx.x;
+  const double* m = mom + (size_t)b * C0_NMOM;
+  double w[C0_K];
+#pragma unroll
+  for (int j = 0; j < C0_K; ++j) w[j] = (double)w0[c * C0_K + j];
+  double s1 = 0.0, s2 = 0.0;
+  int idx = C0_K;
+#pragma unroll
+  for (int j = 0; j < C0_K; ++j) {
+    s1 += w[j] * m[j];
+#pragma unroll
+    for (int k = j; k < C0_K; ++k) {
+      const double r = m[idx++];
+      s2 += (j == k ? 1.0 : 2.0) * w[j] * w[k] * r;
+    }
+  }
+  const double mean = s1 / L0;
+  double var = s2 / L0 - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const double rstd = 1.0 / sqrt(var + 1e-5);
+  const double sc = (double)gamma[c] * rstd;
+  scale[b * C0_OUT + c] = (float)sc;
+  shift[b * C0_OUT + c] = (float)((double)beta[c] - mean * sc);
+}
+
+// ----------------------------------------------------------------------------------------------
+// conv0 + GroupNorm + GELU, written channels-last as fp16 hi (+ lo):  out[b, t, c]
+// grid (ceil(L0/64), B), block 128; each thread owns 4 consecutive channels.
+// ----------------------------------------------------------------------------------------------
+constexpr int C0A_THREADS = 128;
+constexpr int C0A_T = 64;
+
+__global__ void __launch_bounds__(C0A_THREADS)
+conv0_apply_kernel(const float* __restrict__ wav, int t_samp, int L0, const float* __restrict__ w0,
+                   const float* __restrict__ scale, const float* __restrict__ shift, __half* __restrict__ out_hi,
+                   __half* __restrict__ out_lo) {
+  __shared__ float xs[C0A_T * C0_S + C0_K];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * C0A_T;
+  const int nt = min(C0A_T, L0 - t0);
+  const float* w = wav + (size_t)b * t_samp + (size_t)t0 * C0_S;
+  const int nsamp = nt * C0_S + (C0_K - C0_S);
+  for (int i = threadIdx.x; i < nsamp; i += C0A_THREADS) xs[i] = w[i];
+
+  const int c0 = threadIdx.x * 4;
+  float wr[4][C0_K], sc[4], sh[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+#pragma unroll
+    for (int j = 0; j < C0_K; ++j) wr[q][j] = w0[(c0 + q) * C0_K + j];
+    sc[q] = scale[b * C0_OUT + c0 + q];
+    sh[q] = shift[b * C0_OUT + c0 + q];
+  }
+  __syncthreads();
+
+  for (int t = 0; t < nt; ++t) {
+    float x[C0_K];
+#pragma unroll
+    for (int j = 0; j < C0_K; ++j) x[j] = xs[t * C0_S + j];
+    __half hi[4], lo[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float y = 0.0f;
+#pragma unroll
+      for (int j = 0; j < C0_K; ++j) y = fmaf(wr[q][j], x[j], y);
+      split_f16(gelu_erf(fmaf(y, sc[q], sh[q])), hi[q], lo[q]);
+    }
+    const size_t o = ((size_t)b * L0 + t0 + t) * C0_OUT + c0;
+    *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]));
+    if (out_lo) *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]));
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Row LayerNorm (eps 1e-5), one warp per row, D in {512, 768}:
+//    y = LN(x (+ add)) * gamma + beta  ->  fp32 and / or fp16 hi (+ lo)
+// ----------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ add, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, int rows, float* __restrict__ out_f32,
+                      __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+  constexpr int V = D / 128;  // float4 per lane
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = lane_id();
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
+  float4 v[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) v[i] = xr[lane + 32 * i];
+  if (add) {
+    const float4* ar = reinterpret_cast<const float4*>(add + (size_t)row * D);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float4 a = ar[lane + 32 * i];
+      v[i].x += a.x;
+      v[i].y += a.y;
+      v[i].z += a.z;
+      v[i].w += a.w;
+    }
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.0f / D);
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q * (1.0f / D) + 1e-5f);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float4 g = __ldg(g4 + lane + 32 * i), bb = __ldg(b4 + lane + 32 * i);
+    float4 y;
+    y.x = (v[i].x - mean) * rstd * g.x + bb.x;
+    y.y = (v[i].y - mean) * rstd * g.y + bb.y;
+    y.z = (v[i].z - mean) * rstd * g.z + bb.z;
+    y.w = (v[i].w - mean) * rstd * g.w + bb.w;
+    const size_t o = (size_t)row * D + (size_t)(lane + 32 * i) * 4;
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = y;
+    if (out_hi) {
+      __half h0, h1, h2, h3, l0, l1, l2, l3;
+      split_f16(y.x, h0, l0);
+      split_f16(y.y, h1, l1);
+      split_f16(y.z, h2, l2);
+      split_f16(y.w, h3, l3);
+      *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
+      if (out_lo) *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(pack_h2(l0, l1), pack_h2(l2, l3));
+    }
+  }
+}
+
+}  // namespace syl

@@ -1,0 +1,323 @@
+// On-device syllable segmentation and segment-mean pooling.
+// Reference: sylber/utils/segment_utils.py:68-131 (cossim, get_segment) and sylber/model/sylber.py:126-133.
+//
+// The reference is NumPy float32 on the host; segment indices must match it bit for bit, so every
+// floating-point reduction here reproduces NumPy's evaluation ORDER (see oracle/segment_oracle.c):
+//   * a 768-long float32 `.sum()` is NumPy's pairwise sum: 8 blocks of 96 elements, each block reduced by
+//     8 interleaved sequential accumulators and a fixed 3-level tree, blocks combined by a 3-level tree.
+//     A warp holds the 64 accumulators two per lane, so levels map to one in-lane add + 5 xor-shuffles.
+//   * products are rounded before they are summed (no FMA contraction): __fmul_rn / __fadd_rn / __fdiv_rn.
+//   * row means are sequential row-by-row accumulations followed by a division.
+//   * `np.float32 ** .5` on a NumPy *scalar* is libm powf(x, .5f), not sqrtf: powf_half() below replays
+//     glibc's powf (FMA build, as selected on every AVX2 x86-64 host) in fp64, see powf_tables.cuh.
+// The scan over frames is inherently serial per utterance (each decision depends on the running centroid);
+// parallelism comes from one warp per utterance plus the 32 lanes over the 768 features.
+#pragma once
+
+#include "common.cuh"
+#include "powf_tables.cuh"
+
+namespace syl {
+
+constexpr int SEG_D = 768;
+constexpr int SEG_PER_LANE = SEG_D / 32;  // 24 features per lane = 2 accumulators x 12 terms
+
+// element owned by (lane, accumulator a in {0,1}, term m in 0..11) under NumPy's pairwise order
+__device__ __forceinline__ int seg_elem(int lane, int m) { return 96 * (lane >> 2) + 8 * m + 2 * (lane & 3); }
+
+struct LaneVec {
+  float v[SEG_PER_LANE];  // v[2*m + a] = x[seg_elem(lane, m) + a]
+};
+
+__device__ __forceinline__ void lane_load(LaneVec& d, const float* __restrict__ row, int lane) {
+#pragma unroll
+  for (int m = 0; m < 12; ++m) {
+    const float2 t = *reinterpret_cast<const float2*>(row + seg_elem(lane, m));
+    d.v[2 * m] = t.x;
+    d.v[2 * m + 1] = t.y;
+  }
+}
+
+// finish NumPy's pairwise tree from the two in-lane accumulators; result identical in all lanes
+__device__ __forceinline__ float pairwise_finish(float a0, float a1) {
+  float s = __fadd_rn(a0, a1);                                   // r[2k] + r[2k+1]
+#pragma unroll
+  for (int o = 1; o <= 16; o <<= 1) s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
+  return __fadd_rn(0.0f, s);                                     // ndarray.sum() starts from the identity
+}
+
+// NumPy (x*y).sum(-1) over 768 float32
+__device__ __forceinline__ float np_dot768(const LaneVec& x, const LaneVec& y) {
+  float a0 = __fmul_rn(x.v[0], y.v[0]), a1 = __fmul_rn(x.v[1], y.v[1]);
+#pragma unroll
+  for (int m = 1; m < 12; ++m) {
+    a0 = __fadd_rn(a0, __fmul_rn(x.v[2 * m], y.v[2 * m]));
+    a1 = __fadd_rn(a1, __fmul_rn(x.v[2 * m + 1], y.v[2 * m + 1]));
+  }
+  return pairwise_finish(a0, a1);
+}
+
+// two dot products sharing one shuffle tree: (x*y).sum(), (x*x).sum()
+__device__ __forceinline__ void np_dot768_pair(const LaneVec& x, const LaneVec& y, float& xy, float& xx) {
+  float a0 = __fmul_rn(x.v[0], y.v[0]), a1 = __fmul_rn(x.v[1], y.v[1]);
+  float b0 = __fmul_rn(x.v[0], x.v[0]), b1 = __fmul_rn(x.v[1], x.v[1]);
+#pragma unroll
+  for (int m = 1; m < 12; ++m) {
+    a0 = __fadd_rn(a0, __fmul_rn(x.v[2 * m], y.v[2 * m]));
+    a1 = __fadd_rn(a1, __fmul_rn(x.v[2 * m + 1], y.v[2 * m + 1]));
+    b0 = __fadd_rn(b0, __fmul_rn(x.v[2 * m], x.v[2 * m]));
+    b1 = __fadd_rn(b1, __fmul_rn(x.v[2 * m + 1], x.v[2 * m + 1]));
+  }
+  float s = __fadd_rn(a0, a1), q = __fadd_rn(b0, b1);
+#pragma unroll
+  for (int o = 1; o <= 16; o <<= 1) {
+    s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
+    q = __fadd_rn(q, __shfl_xor_sync(0xffffffffu, q, o));
+  }
+  xy = __fadd_rn(0.0f, s);
+  xx = __fadd_rn(0.0f, q);
+}
+
+// NumPy pairwise sum of a contiguous float vector read by ONE thread (used for the short sweep sums)
+__device__ float np_pairwise_serial(const float* a, int n) {
+  if (n < 8) {
+    float r = -0.0f;
+    for (int i = 0; i < n; ++i) r = __fadd_rn(r, a[i]);
+    return r;
+  }
+  if (n <= 128) {
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], a[i + j]);
+    }
+    float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                          __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __fadd_rn(res, a[i]);
+    return res;
+  }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  return __fadd_rn(np_pairwise_serial(a, n2), np_pairwise_serial(a + n2, n - n2));
+}
+__device__ __forceinline__ float np_sum_serial(const float* a, int n) { return __fadd_rn(0.0f, np_pairwise_serial(a, n)); }
+
+// ----------------------------------------------------------------------------------------------
+// per-frame squared norms + eps, one warp per frame:  nsq[i] = (x_i**2).sum() + 1e-8   (float32)
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+frame_sqnorm_kernel(const float* __restrict__ states, int rows, float* __restrict__ nsq) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = lane_id();
+  LaneVec x;
+  lane_load(x, states + (size_t)row * SEG_D, lane);
+  const float s = np_dot768(x, x);
+  if (lane == 0) nsq[row] = __fadd_rn(s, 1e-8f);
+}
+
+// mean over rows [s, e) in NumPy order; every lane keeps its 24 features
+__device__ __forceinline__ void lane_mean_rows(LaneVec& acc, const float* __restrict__ states, int s, int e, int lane) {
+  if (e <= s) {
+#pragma unroll
+    for (int k = 0; k < SEG_PER_LANE; ++k) acc.v[k] = __int_as_float(0x7fc00000);
+    return;
+  }
+  lane_load(acc, states + (size_t)s * SEG_D, lane);
+  for (int r = s + 1; r < e; ++r) {
+    LaneVec x;
+    lane_load(x, states + (size_t)r * SEG_D, lane);
+#pragma unroll
+    for (int k = 0; k < SEG_PER_LANE; ++k) acc.v[k] = __fadd_rn(acc.v[k], x.v[k]);
+  }
+  const float fn = (float)(e - s);
+#pragma unroll
+  for (int k = 0; k < SEG_PER_LANE; ++k) acc.v[k] = __fdiv_rn(acc.v[k], fn);
+}
+
+// ----------------------------------------------------------------------------------------------
+// segmentation: one warp per utterance.
+//   states  [B, T, 768] fp32           nsq [B, T]  from frame_sqnorm_kernel
+//   seg     [B, max_seg, 2] int32 out  seg_count [B] out
+//   scratch [B, 6*(T+1)] int32/float workspace (segment starts/ends/dead flags, boundaries, sweep sims)
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+segment_kernel(const float* __restrict__ states_all, const float* __restrict__ nsq_all, int T, float thr_norm,
+               float thr_merge, int32_t* __restrict__ seg_all, int32_t* __restrict__ seg_count, int max_seg,
+               int32_t* __restrict__ scratch_all) {
+  const int b = blockIdx.x;
+  const int lane = lane_id();
+  const float* states = states_all + (size_t)b * T * SEG_D;
+  const float* nsq = nsq_all + (size_t)b * T;
+  int32_t* scratch = scratch_all + (size_t)b * 6 * (T + 1);
+  int32_t* seg_s = scratch;
+  int32_t* seg_e = scratch + (T + 1);
+  int32_t* mid_bd = scratch + 2 * (T + 1);
+  int32_t* mid_seg = scratch + 3 * (T + 1);
+  float* sim_prev = reinterpret_cast<float*>(scratch + 4 * (T + 1));
+  float* sim_next = reinterpret_cast<float*>(scratch + 5 * (T + 1));
+
+  int nseg = 0, nmid = 0;
+  // ---- phase 1: greedy scan (segment_utils.py:79-108) ----
+  {
+    LaneVec curr;
+    float curr_sq = 0.0f;  // (curr**2).sum() + 1e-8
+    int cnt = 0, s = -1;
+    for (int i = 0; i < T; ++i) {
+      const float xsq = nsq[i];
+      const bool on = __fsqrt_rn(xsq) >= thr_norm;    // array path: `** .5` on an ndarray is sqrt
+      if (!on) {
+        if (s > -1) {
+          if (lane == 0) { seg_s[nseg] = s; seg_e[nseg] = i; }
+          ++nseg;
+        }
+        s = -1;
+        cnt = 0;
+        continue;
+      }
+      LaneVec x;
+      lane_load(x, states + (size_t)i * SEG_D, lane);
+      if (cnt == 0) {
+        curr = x;
+        curr_sq = xsq;
+        cnt = 1;
+        s = i;
+        continue;
+      }
+      const float xy = np_dot768(curr, x);
+      const float sim = __fdiv_rn(__fdiv_rn(xy, powf_half(curr_sq)), powf_half(xsq));   // scalar path: powf
+      if (sim >= thr_merge) {
+        const float fc = (float)cnt, fc1 = (float)(cnt + 1);
+#pragma unroll
+        for (int k = 0; k < SEG_PER_LANE; ++k)
+          curr.v[k] = __fdiv_rn(__fadd_rn(__fmul_rn(curr.v[k], fc), x.v[k]), fc1);
+        curr_sq = __fadd_rn(np_dot768(curr, curr), 1e-8f);
+        cnt += 1;
+      } else {
+        curr = x;
+        curr_sq = xsq;
+        cnt += 1;   // not reset: reference quirk (segment_utils.py:103)
+        if (lane == 0) { seg_s[nseg] = s; seg_e[nseg] = i; mid_bd[nmid] = i; mid_seg[nmid] = nseg; }
+        ++nseg;
+        ++nmid;
+        s = i;
+      }
+    }
+    if (s > -1) {
+      if (lane == 0) { seg_s[nseg] = s; seg_e[nseg] = T; }
+      ++nseg;
+    }
+  }
+  __syncwarp();
+
+  // ---- phase 2: boundary merge / refinement, in order (segment_utils.py:110-128) ----
+  // dead flags are kept as negative ends to avoid another array: seg_e < 0 marks an absorbed segment
+  for (int m = 0; m < nmid; ++m) {
+    const int bd = mid_bd[m], a = mid_seg[m];
+    if (a >= nseg - 1) continue;
+    const int bsg = a + 1;
+    const int as = seg_s[a], ae = seg_e[a], bs = seg_s[bsg], be = seg_e[bsg];
+    LaneVec ca, cb;
+    lane_mean_rows(ca, states, as, ae, lane);
+    lane_mean_rows(cb, states, bs, be, lane);
+    float ab, aa, bb, tmp;
+    np_dot768_pair(ca, cb, ab, aa);
+    np_dot768_pair(cb, cb, bb, tmp);
+    aa = __fadd_rn(aa, 1e-8f);
+    bb = __fadd_rn(bb, 1e-8f);
+    const float simc = __fdiv_rn(__fdiv_rn(ab, powf_half(aa)), powf_half(bb));
+    if (simc >= thr_merge) {
+      __syncwarp();
+      if (lane == 0) { seg_s[bsg] = as; seg_e[a] = -1 - ae; }
+      __syncwarp();
+      continue;
+    }
+    const int la = ae - as, lb = be - bs;
+    const int lo = max(as, bd - max(1, la / 2));
+    const int hi = min(be, bd + max(1, lb / 2));
+    const int W = hi - lo;
+    const float na = __fsqrt_rn(aa), nb = __fsqrt_rn(bb);   // 2-D path of cossim: sqrt
+    for (int r = 0; r < W; ++r) {
+      LaneVec x;
+      lane_load(x, states + (size_t)(lo + r) * SEG_D, lane);
+      float xa, xx, xb;
+      np_dot768_pair(x, ca, xa, xx);
+      xb = np_dot768(x, cb);
+      const float nx = __fsqrt_rn(__fadd_rn(xx, 1e-8f));
+      if (lane == 0) {
+        sim_prev[r] = __fdiv_rn(__fdiv_rn(xa, nx), na);
+        sim_next[r] = __fdiv_rn(__fdiv_rn(xb, nx), nb);
+      }
+    }
+    __syncwarp();
+    float best_v = 0.0f;
+    int best_i = 0x7fffffff;
+    for (int i = lane; i < W; i += 32) {
+      const float v = __fadd_rn(np_sum_serial(sim_prev, i), np_sum_serial(sim_next + i, W - i));
+      if (best_i == 0x7fffffff || v > best_v) { best_v = v; best_i = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (oi != 0x7fffffff && (best_i == 0x7fffffff || ov > best_v || (ov == best_v && oi < best_i))) {
+        best_v = ov;
+        best_i = oi;
+      }
+    }
+    const int opt = lo + best_i;
+    __syncwarp();
+    if (lane == 0) { seg_e[a] = opt; seg_s[bsg] = opt; }
+    __syncwarp();
+  }
+
+  // ---- phase 3: drop absorbed segments (segment_utils.py:130-131) ----
+  if (lane == 0) {
+    int n = 0;
+    int32_t* out = seg_all + (size_t)b * max_seg * 2;
+    for (int i = 0; i < nseg; ++i) {
+      if (seg_e[i] < 0) continue;
+      if (n < max_seg) { out[2 * n] = seg_s[i]; out[2 * n + 1] = seg_e[i]; }
+      ++n;
+    }
+    seg_count[b] = n;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// segment features (sylber.py:133): mean of the hidden states over each segment, NumPy order.
+// grid (max_seg, B), block 192: each thread owns 4 consecutive features.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192)
+segment_pool_kernel(const float* __restrict__ states_all, int T, const int32_t* __restrict__ seg_all,
+                    const int32_t* __restrict__ seg_count, int max_seg, float* __restrict__ feat_all) {
+  const int b = blockIdx.y, sidx = blockIdx.x;
+  if (sidx >= min(seg_count[b], max_seg)) return;
+  const int s = seg_all[((size_t)b * max_seg + sidx) * 2], e = seg_all[((size_t)b * max_seg + sidx) * 2 + 1];
+  const float* st = states_all + (size_t)b * T * SEG_D + threadIdx.x * 4;
+  float4 acc;
+  if (e <= s) {
+    const float nan = __int_as_float(0x7fc00000);
+    acc = make_float4(nan, nan, nan, nan);
+  } else {
+    acc = *reinterpret_cast<const float4*>(st + (size_t)s * SEG_D);
+    for (int r = s + 1; r < e; ++r) {
+      const float4 x = *reinterpret_cast<const float4*>(st + (size_t)r * SEG_D);
+      acc.x = __fadd_rn(acc.x, x.x);
+      acc.y = __fadd_rn(acc.y, x.y);
+      acc.z = __fadd_rn(acc.z, x.z);
+      acc.w = __fadd_rn(acc.w, x.w);
+    }
+    const float fn = (float)(e - s);
+    acc.x = __fdiv_rn(acc.x, fn);
+    acc.y = __fdiv_rn(acc.y, fn);
+    acc.z = __fdiv_rn(acc.z, fn);
+    acc.w = __fdiv_rn(acc.w, fn);
+  }
+  *reinterpret_cast<float4*>(feat_all + ((size_t)b * max_seg + sidx) * SEG_D + threadIdx.x * 4) = acc;
+}
+
+}  // namespace syl
