@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Benchmark of the Segmenter forward path (BASELINE.json: audio frames/s on 10 s, 16 kHz clips).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--layers 9] [--mode parity]
+
+One "step" = one pass of the hot path (conv front end -> 9-layer encoder -> segmentation -> segment pooling)
+over one batch of synthetic audio.  Workload at every N: BASELINE.json configs[1] per GPU - batch 32 x 10 s of
+N(0,1) "audio" (the distribution after the reference's (w-mean)/std), hubert-base architecture with the
+reference's 9 encoder layers, synthetic weights (no checkpoint exists offline).  Weak scaling: each rank owns
+32 utterances; the only collective is the all-gather of the fixed-stride segment table.
+
+JSON line (rank 0): value = frames/s with inputs resident in HBM (CUDA events, max over ranks);
+e2e = the same through Segmenter.__call__ from host tensors (H2D + D2H inside the timed region);
+roofline = dominant stage against MEASURED_PEAKS.json; stages = per-stage device time and achieved rates;
+cpu_baseline = the CPU oracle port (torch CPU ops + NumPy segmentation, what the reference executes) on this
+box's host cores.  `--impl reference` times that CPU path alone.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "audio frames/sec (16 kHz, 10 s clips)"
+UNIT = "frames/s"
+N_SAMPLES = 160000
+BATCH_PER_GPU = 32
+THR_NORM, THR_MERGE = 2.6, 0.8
+CONV_K = (10, 3, 3, 3, 3, 2, 2)
+CONV_S = (5, 2, 2, 2, 2, 2, 2)
+
+
+def conv_lengths(n):
+    out = []
+    for k, s in zip(CONV_K, CONV_S):
+        n = (n - k) // s + 1
+        out.append(n)
+    return out
+
+
+def stage_flops(n_samples, layers):
+    """Algorithmic FLOPs (2*MAC) per utterance and stage."""
+    L = conv_lengths(n_samples)
+    T = L[6]
+    return {
+        "conv0_gn_gelu": 2 * 512 * 10 * L[0],
+        "conv1_6_gemm": 2 * 512 * 512 * (3 * (L[1] + L[2] + L[3] + L[4]) + 2 * (L[5] + L[6])),
+        "feature_proj_gemm": 2 * T * 512 * 768,
+        "pos_conv_gemm": 2 * T * 768 * 48 * 128,
+        "qkv_gemm": layers * 2 * T * 768 * 2304,
+        "attention": layers * 4 * T * T * 768,
+        "out_proj_gemm": layers * 2 * T * 768 * 768,
+        "ffn1_gemm": layers * 2 * T * 768 * 3072,
+        "ffn2_gemm": layers * 2 * T * 768 * 3072,
+    }, T, L
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "tf_burst": p["bf16_tflops"], "tf_sustained": p["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [x for x in sm if x > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU path (oracle port): what the reference executes, restated so it can run on the GPU box
+# --------------------------------------------------------------------------------------------------
+def cpu_step(sd, wav, lens, layers):
+    from oracle.hubert_ref import hubert_forward
+    from oracle import segment_ref
+    hidden = hubert_forward(sd, wav, lens, layers).numpy()
+    outs = []
+    for states in hidden:
+        seg = segment_ref.get_segment(states, THR_NORM, THR_MERGE)
+        outs.append(segment_ref.package(states, seg, in_second=True))
+    return outs
+
+
+def time_cpu(sd, layers, batch, steps, warmup, seed=1):
+    torch.set_num_threads(os.cpu_count())
+    g = torch.Generator().manual_seed(seed)
+    wav = torch.randn(batch, N_SAMPLES, generator=g)
+    lens = [N_SAMPLES] * batch
+    T = conv_lengths(N_SAMPLES)[6]
+    for _ in range(warmup):
+        cpu_step(sd, wav, lens, layers)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        cpu_step(sd, wav, lens, layers)
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return batch * T * steps / total, total / steps * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from sylber_b200.weights import syllabic_test_state_dict
+    sd = syllabic_test_state_dict(args.layers, 0)
+    batch = 4
+    fps, ms = time_cpu(sd, args.layers, batch, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"batch=32 synthetic 10 s 16 kHz wav, sylber_base ({args.layers}L/768d)",
+                   "note": "CPU path of the reference restated in oracle/ (torch CPU conv/linear/SDPA-equivalent ops + "
+                           "NumPy get_segment); each step is a bounded sample of 4 clips of the workload"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{batch} x 10 s clips per step, {args.steps} steps, torch {torch.__version__} fp32, "
+                                   f"os.cpu_count()={os.cpu_count()}"},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from sylber_b200 import Segmenter
+    from sylber_b200.weights import syllabic_test_state_dict
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the GPU arm has no CPU fallback (use --impl reference for the CPU path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    layers = args.layers
+    sd = syllabic_test_state_dict(layers, 0)
+    seg = Segmenter(model_ckpt=None, state_dict=sd, encoding_layer=layers, device=f"cuda:{local}", mode=args.mode,
+                    max_batch=BATCH_PER_GPU)
+    eng = seg._engine
+    B = BATCH_PER_GPU
+    flops, T, L = stage_flops(N_SAMPLES, layers)
+    g = torch.Generator().manual_seed(1)
+    wav_all = torch.randn(B * world, N_SAMPLES, generator=g) if world * B <= 256 else None
+    wav_host = wav_all[rank * B:(rank + 1) * B].contiguous()
+    wav_dev = wav_host.to(dev)
+    n_dev = torch.full((B,), N_SAMPLES, dtype=torch.int32, device=dev)
+    thr_n, thr_m = np.float32(THR_NORM), np.float32(THR_MERGE)
+    gathered_cnt = torch.empty((world * B,), dtype=torch.int32, device=dev) if world > 1 else None
+    gathered_seg = torch.empty((world * B, T, 2), dtype=torch.int32, device=dev) if world > 1 else None
+
+    def step():
+        hidden, sg, cnt, feat = eng.forward(wav_dev, n_dev, thr_n, thr_m)
+        if world > 1:  # the one exchange of the path: the fixed-stride segment table
+            dist.all_gather_into_tensor(gathered_cnt, cnt)
+            dist.all_gather_into_tensor(gathered_seg, sg)
+        return hidden, sg, cnt, feat
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing (value) ----------------
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng.profile(True)
+    eng.profile_read()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    prof = eng.profile_read()
+    eng.profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    frames_per_step = world * B * T
+    value = frames_per_step * args.steps / (ms_total / 1e3)
+    seg_counts = out[2].cpu().numpy()
+
+    # ---------------- end-to-end through Segmenter.__call__ from host tensors ----------------
+    wav_list = [wav_host[i:i + 1] for i in range(B)]
+    for _ in range(3):
+        res = seg(wav=wav_list, in_second=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = seg(wav=wav_list, in_second=True)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = frames_per_step * args.steps / float(t.item())
+    h2d = B * N_SAMPLES * 4 + B * 4
+    d2h = B * T * 768 * 4 + B * 4 + sum(int(np.asarray(r["segments"]).size) * 4 + int(np.asarray(r["segment_features"]).size) * 4
+                                        for r in res)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline bookkeeping ----------------
+    peaks = load_peaks()
+    stages = {}
+    for name, (ms, cnt) in prof.items():
+        if cnt == 0:
+            continue
+        ms_step = ms / args.steps
+        entry = {"ms_per_step": round(ms_step, 4), "share": round(ms / ms_total, 4)}
+        if name in flops and name != "conv0_gn_gelu":
+            tf = flops[name] * B / (ms_step * 1e-3) / 1e12
+            entry.update({"bound": "tensor", "achieved_tflops": round(tf, 1), "frac": round(tf / peaks["tf_sustained"], 4)})
+        stages[name] = entry
+    # HBM-bound stages: algorithmic bytes
+    if "conv0_gn_gelu" in stages:
+        by = B * (2 * N_SAMPLES * 4 + L[0] * 512 * 2 * 2)      # wav read twice (stats + apply), hi+lo fp16 written
+        gbs = by / (stages["conv0_gn_gelu"]["ms_per_step"] * 1e-3) / 1e9
+        stages["conv0_gn_gelu"].update({"bound": "hbm", "achieved_gbs": round(gbs, 1), "frac": round(gbs / peaks["hbm_gbs"], 4)})
+    if "layernorm" in stages:
+        M = B * T
+        by = M * 512 * (4 + 4) + (1 + 2 * layers) * M * 768 * (4 + 4 + 2) + M * 768 * 4
+        gbs = by / (stages["layernorm"]["ms_per_step"] * 1e-3) / 1e9
+        stages["layernorm"].update({"bound": "hbm", "achieved_gbs": round(gbs, 1), "frac": round(gbs / peaks["hbm_gbs"], 4)})
+    if "attention" in stages:
+        by = layers * B * 4 * T * 768 * 2
+        stages["attention"]["hbm_gbs"] = round(by / (stages["attention"]["ms_per_step"] * 1e-3) / 1e9, 1)
+        stages["attention"]["hbm_frac"] = round(stages["attention"]["hbm_gbs"] / peaks["hbm_gbs"], 4)
+    enc = ["qkv_gemm", "attention", "out_proj_gemm", "ffn1_gemm", "ffn2_gemm"]
+    enc_ms = sum(stages[s]["ms_per_step"] for s in enc if s in stages)
+    enc_tf = sum(flops[s] for s in enc) * B / (enc_ms * 1e-3) / 1e12 if enc_ms else 0.0
+    tensor_stages = [s for s in stages if stages[s].get("bound") == "tensor"]
+    dom = max(tensor_stages, key=lambda s: stages[s]["ms_per_step"])
+    kernel_of = {"attention": "attention_kernel", "pos_conv_gemm": "gemm_tc_kernel<48>"}
+    roofline = {
+        "bound": "tensor", "kernel": kernel_of.get(dom, "gemm_tc_kernel<256>"), "stage": dom,
+        "achieved": stages[dom]["achieved_tflops"], "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+        "frac": stages[dom]["frac"], "traffic": None,
+        "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); fp16 and bf16 share the tensor rate",
+        "algorithmic_flops_per_step": flops[dom] * B,
+        "attn_mlp_path": {"achieved": round(enc_tf, 1), "frac": round(enc_tf / peaks["tf_sustained"], 4), "unit": "TFLOP/s",
+                          "ms_per_step": round(enc_ms, 4)},
+        "attention_hbm": {"achieved": stages.get("attention", {}).get("hbm_gbs"), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                          "frac": stages.get("attention", {}).get("hbm_frac")},
+    }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 operands (conv stack + projection split hi/lo, 3 tensor-core passes), f32 accumulate/LN/softmax"
+                 if args.mode == "parity" else f"f16 ({args.mode})",
+        "data": "synthetic",
+        "config": {"workload": f"batch=32 synthetic 10 s 16 kHz wav per GPU, sylber_base ({layers}L/768d), 1xB200 per rank",
+                   "frames_per_clip": T, "batch_per_gpu": B, "mode": args.mode, "parallelism": f"dp{world} by utterance",
+                   "l2": "per-step working set (~4 GB of activations) exceeds the 126 MB L2; no explicit flush",
+                   "segments_per_clip_mean": float(seg_counts.mean())},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s / args.steps * 1e3},
+        "gpu_launches": eng.launch_count(True) * args.steps,
+        "clocks": clocks,
+        "roofline": roofline,
+        "stages": stages,
+    }
+    if world == 1 and not args.no_cpu:
+        torch.cuda.synchronize()
+        fps, ms = time_cpu(sd, layers, 8, 2, 1)
+        line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"8 x 10 s clips, 1 warm-up + 2 timed passes of oracle/ (torch CPU fp32 + NumPy "
+                                          f"get_segment), os.cpu_count()={os.cpu_count()}", "ms_per_step": ms}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--layers", type=int, default=9)
+    ap.add_argument("--mode", default="parity", choices=["parity", "fast", "exact"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

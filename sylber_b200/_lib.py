@@ -12,7 +12,7 @@ _SO = os.path.join(_PKG, "libsylber_b200.so")
 
 SYL_SPLIT_CONV, SYL_SPLIT_PROJ, SYL_SPLIT_ENC = 1, 2, 4
 MODES = {
-    "parity": SYL_SPLIT_CONV,
+    "parity": SYL_SPLIT_CONV | SYL_SPLIT_PROJ,
     "fast": 0,
     "exact": SYL_SPLIT_CONV | SYL_SPLIT_PROJ | SYL_SPLIT_ENC,
 }
@@ -44,6 +44,10 @@ SIGNATURES = {
     "syl_read_stage": (_c_int, [_c_void_p, ctypes.c_char_p, _c_void_p, _c_size_t, _c_void_p]),
     "syl_set_active_layers": (_c_int, [_c_void_p, _c_int]),
     "syl_forward_launch_count": (_c_int, [_c_void_p, _c_int]),
+    "syl_num_stages": (_c_int, []),
+    "syl_stage_name": (ctypes.c_char_p, [_c_int]),
+    "syl_profile_enable": (_c_int, [_c_void_p, _c_int]),
+    "syl_profile_read": (_c_int, [_c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
 }
 
 _LIB = None

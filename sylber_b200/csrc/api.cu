@@ -35,6 +35,15 @@ constexpr int kPosCg = 48;     // channels per group
 
 std::string g_create_error;
 
+// device-time profiling by stage (CUDA events on the launch stream, enabled by syl_profile_enable)
+enum Stage { ST_CONV0 = 0, ST_CONV, ST_LN, ST_PROJ, ST_POS, ST_QKV, ST_ATTN, ST_OUT, ST_FFN1, ST_FFN2, ST_SEG, ST_COUNT };
+const char* const kStageNames[ST_COUNT] = {"conv0_gn_gelu", "conv1_6_gemm", "layernorm", "feature_proj_gemm", "pos_conv_gemm",
+                                           "qkv_gemm", "attention", "out_proj_gemm", "ffn1_gemm", "ffn2_gemm", "segment_pool"};
+struct ProfRec {
+  int stage;
+  cudaEvent_t a, b;
+};
+
 // ------------------------------------------------------------------------------------------------
 // driver entry point for cuTensorMapEncodeTiled (no link-time dependency on libcuda)
 // ------------------------------------------------------------------------------------------------
@@ -243,6 +252,10 @@ struct syl_handle {
   std::vector<LayerW> layers;
   Plan plan;
   int sm_count = 148;
+  bool profile = false;
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> pool;
+  size_t pool_used = 0;
 };
 
 namespace {
@@ -256,6 +269,31 @@ int fail(syl_handle* h, int code, const char* fmt, ...) {
   if (h) h->err = buf; else g_create_error = buf;
   return code;
 }
+
+cudaEvent_t prof_event(syl_handle* h) {
+  if (h->pool_used == h->pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    h->pool.push_back(e);
+  }
+  return h->pool[h->pool_used++];
+}
+
+struct StageTimer {
+  syl_handle* h;
+  cudaStream_t st;
+  cudaEvent_t b = nullptr;
+  StageTimer(syl_handle* h_, int stage, cudaStream_t st_) : h(h_), st(st_) {
+    if (!h->profile) return;
+    cudaEvent_t a = prof_event(h);
+    b = prof_event(h);
+    cudaEventRecord(a, st);
+    h->recs.push_back({stage, a, b});
+  }
+  ~StageTimer() {
+    if (b) cudaEventRecord(b, st);
+  }
+};
 
 #define CUDA_TRY(h, expr)                                                                        \
   do {                                                                                           \
@@ -612,6 +650,8 @@ int run_frontend(syl_handle* h, const float* wav, cudaStream_t st) {
   const WsLayout& L = pl.lay;
   void* ws = pl.ws;
   const int B = pl.batch, L0 = L.L[0];
+  {
+  StageTimer tm(h, ST_CONV0, st);
   CUDA_TRY(h, cudaMemsetAsync(at<double>(ws, L.mom), 0, (size_t)B * C0_NMOM * sizeof(double), st));
   conv0_moments_kernel<<<dim3((L0 + MOM_T_PER_BLOCK - 1) / MOM_T_PER_BLOCK, B), MOM_THREADS, 0, st>>>(
       wav, pl.t_samp, L0, at<double>(ws, L.mom));
@@ -620,7 +660,9 @@ int run_frontend(syl_handle* h, const float* wav, cudaStream_t st) {
   conv0_apply_kernel<<<dim3((L0 + C0A_T - 1) / C0A_T, B), C0A_THREADS, 0, st>>>(
       wav, pl.t_samp, L0, h->conv0_w, at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift),
       at<__half>(ws, L.act_hi[0]), (h->mode & SYL_SPLIT_CONV) ? at<__half>(ws, L.act_lo[0]) : nullptr);
+  }
   CUDA_TRY(h, cudaGetLastError());
+  StageTimer tm(h, ST_CONV, st);
   for (int i = 0; i < 6; ++i) {
     int rc = launch_gemm(h, pl.conv[i], st, h->sm_count);
     if (rc) return rc;
@@ -636,7 +678,10 @@ int run_layer(syl_handle* h, int l, float* h_out, cudaStream_t st) {
   const LayerW& w = h->layers[l];
   const bool split_enc = h->mode & SYL_SPLIT_ENC;
   int rc;
-  if ((rc = launch_gemm(h, pl.qkv[l], st, h->sm_count))) return rc;
+  {
+    StageTimer tm(h, ST_QKV, st);
+    if ((rc = launch_gemm(h, pl.qkv[l], st, h->sm_count))) return rc;
+  }
   AttnParams ap;
   ap.T = T;
   ap.heads = kHeads;
@@ -644,15 +689,33 @@ int run_layer(syl_handle* h, int l, float* h_out, cudaStream_t st) {
   ap.kv_len = at<int32_t>(ws, L.valid);
   ap.out_hi = at<__half>(ws, L.ctx_hi);
   ap.out_lo = split_enc ? at<__half>(ws, L.ctx_lo) : nullptr;
-  attention_kernel<<<dim3((T + ATT_BQ - 1) / ATT_BQ, kHeads, B), ATT_THREADS, ATT_SMEM_TOTAL, st>>>(pl.attn_map, ap);
+  {
+    StageTimer tm(h, ST_ATTN, st);
+    attention_kernel<<<dim3((T + ATT_BQ - 1) / ATT_BQ, kHeads, B), ATT_THREADS, ATT_SMEM_TOTAL, st>>>(pl.attn_map, ap);
+  }
   CUDA_TRY(h, cudaGetLastError());
-  if ((rc = launch_gemm(h, pl.out[l], st, h->sm_count))) return rc;
-  launch_ln<kH>(at<float>(ws, L.pre), nullptr, w.ln1_g, w.ln1_b, M, at<float>(ws, L.h), at<__half>(ws, L.h16_hi),
-                split_enc ? at<__half>(ws, L.h16_lo) : nullptr, st);
-  if ((rc = launch_gemm(h, pl.ffn1[l], st, h->sm_count))) return rc;
-  if ((rc = launch_gemm(h, pl.ffn2[l], st, h->sm_count))) return rc;
-  launch_ln<kH>(at<float>(ws, L.pre), nullptr, w.ln2_g, w.ln2_b, M, h_out, at<__half>(ws, L.h16_hi),
-                split_enc ? at<__half>(ws, L.h16_lo) : nullptr, st);
+  {
+    StageTimer tm(h, ST_OUT, st);
+    if ((rc = launch_gemm(h, pl.out[l], st, h->sm_count))) return rc;
+  }
+  {
+    StageTimer tm(h, ST_LN, st);
+    launch_ln<kH>(at<float>(ws, L.pre), nullptr, w.ln1_g, w.ln1_b, M, at<float>(ws, L.h), at<__half>(ws, L.h16_hi),
+                  split_enc ? at<__half>(ws, L.h16_lo) : nullptr, st);
+  }
+  {
+    StageTimer tm(h, ST_FFN1, st);
+    if ((rc = launch_gemm(h, pl.ffn1[l], st, h->sm_count))) return rc;
+  }
+  {
+    StageTimer tm(h, ST_FFN2, st);
+    if ((rc = launch_gemm(h, pl.ffn2[l], st, h->sm_count))) return rc;
+  }
+  {
+    StageTimer tm(h, ST_LN, st);
+    launch_ln<kH>(at<float>(ws, L.pre), nullptr, w.ln2_g, w.ln2_b, M, h_out, at<__half>(ws, L.h16_hi),
+                  split_enc ? at<__half>(ws, L.h16_lo) : nullptr, st);
+  }
   CUDA_TRY(h, cudaGetLastError());
   return SYL_OK;
 }
@@ -707,6 +770,7 @@ void syl_destroy(syl_handle* h) {
   cudaSetDevice(h->device);
   for (auto& kv : h->raw) cudaFree(kv.second.first);
   for (void* p : h->owned) cudaFree(p);
+  for (cudaEvent_t e : h->pool) cudaEventDestroy(e);
   delete h;
 }
 
@@ -847,15 +911,27 @@ int syl_forward(syl_handle* h, const float* wav, const int32_t* n_samples, int b
   else
     fill_i32_kernel<<<(batch + 127) / 128, 128, 0, st>>>(at<int32_t>(workspace, L.valid), batch, T);
   if ((rc = run_frontend(h, wav, st))) return rc;
-  launch_ln<kC>(at<float>(workspace, L.conv6), nullptr, h->fp_ln_g, h->fp_ln_b, M, nullptr, at<__half>(workspace, L.ln_hi),
-                split_proj ? at<__half>(workspace, L.ln_lo) : nullptr, st);
-  if ((rc = launch_gemm(h, pl.proj, st, h->sm_count))) return rc;
-  if ((rc = launch_gemm(h, pl.pos, st, h->sm_count))) return rc;
+  {
+    StageTimer tm(h, ST_LN, st);
+    launch_ln<kC>(at<float>(workspace, L.conv6), nullptr, h->fp_ln_g, h->fp_ln_b, M, nullptr, at<__half>(workspace, L.ln_hi),
+                  split_proj ? at<__half>(workspace, L.ln_lo) : nullptr, st);
+  }
+  {
+    StageTimer tm(h, ST_PROJ, st);
+    if ((rc = launch_gemm(h, pl.proj, st, h->sm_count))) return rc;
+  }
+  {
+    StageTimer tm(h, ST_POS, st);
+    if ((rc = launch_gemm(h, pl.pos, st, h->sm_count))) return rc;
+  }
   const int nl = (h->active_layers >= 0 && h->active_layers < h->n_layers) ? h->active_layers : h->n_layers;
   // h = LN(h + pos)   (modeling_hubert.py:441-442); with zero layers this is already the output
-  launch_ln<kH>(at<float>(workspace, L.h), at<float>(workspace, L.pos), h->enc_ln_g, h->enc_ln_b, M,
-                nl == 0 ? hidden : at<float>(workspace, L.h), at<__half>(workspace, L.h16_hi),
-                split_enc ? at<__half>(workspace, L.h16_lo) : nullptr, st);
+  {
+    StageTimer tm(h, ST_LN, st);
+    launch_ln<kH>(at<float>(workspace, L.h), at<float>(workspace, L.pos), h->enc_ln_g, h->enc_ln_b, M,
+                  nl == 0 ? hidden : at<float>(workspace, L.h), at<__half>(workspace, L.h16_hi),
+                  split_enc ? at<__half>(workspace, L.h16_lo) : nullptr, st);
+  }
   CUDA_TRY(h, cudaGetLastError());
   for (int l = 0; l < nl; ++l) {
     float* out = (l == nl - 1) ? hidden : at<float>(workspace, L.h);
@@ -863,6 +939,7 @@ int syl_forward(syl_handle* h, const float* wav, const int32_t* n_samples, int b
     if ((rc = run_layer(h, l, out, st))) return rc;
   }
   if (seg) {
+    StageTimer tm(h, ST_SEG, st);
     rc = run_segment(hidden, batch, T, thr_norm, thr_merge, seg, seg_count, seg_feat, max_seg,
                      at<float>(workspace, L.nsq), at<int32_t>(workspace, L.seg_scratch), st);
     if (rc) return fail(h, rc, "segmentation launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1017,6 +1094,34 @@ int syl_powf_half(const float* x, float* y, int64_t n, void* stream) {
   if (!x || !y || n <= 0) return SYL_E_ARG;
   powf_half_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, n);
   return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
+}
+
+int syl_num_stages(void) { return ST_COUNT; }
+
+const char* syl_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : ""; }
+
+int syl_profile_enable(syl_handle* h, int on) {
+  if (!h) return SYL_E_ARG;
+  h->profile = on != 0;
+  return SYL_OK;
+}
+
+int syl_profile_read(syl_handle* h, float* ms, int* counts) {
+  if (!h || !ms || !counts) return SYL_E_ARG;
+  for (int i = 0; i < ST_COUNT; ++i) {
+    ms[i] = 0.0f;
+    counts[i] = 0;
+  }
+  for (const ProfRec& r : h->recs) {
+    CUDA_TRY(h, cudaEventSynchronize(r.b));
+    float t = 0.0f;
+    CUDA_TRY(h, cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.stage] += t;
+    counts[r.stage] += 1;
+  }
+  h->recs.clear();
+  h->pool_used = 0;
+  return SYL_OK;
 }
 
 int syl_read_stage(syl_handle* h, const char* name, float* out, size_t n_floats, void* stream) {

@@ -110,6 +110,17 @@ class _Engine:
     def set_active_layers(self, n):
         _lib.check(self.lib, self.handle, self.lib.syl_set_active_layers(self.handle, int(n)), "syl_set_active_layers")
 
+    def profile(self, on):
+        _lib.check(self.lib, self.handle, self.lib.syl_profile_enable(self.handle, int(bool(on))), "syl_profile_enable")
+
+    def profile_read(self):
+        """{stage name: (milliseconds, regions)} accumulated since the previous read."""
+        n = self.lib.syl_num_stages()
+        ms = (ctypes.c_float * n)()
+        cnt = (ctypes.c_int * n)()
+        _lib.check(self.lib, self.handle, self.lib.syl_profile_read(self.handle, ms, cnt), "syl_profile_read")
+        return {self.lib.syl_stage_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
+
     def launch_count(self, with_segmentation=True):
         return int(self.lib.syl_forward_launch_count(self.handle, int(with_segmentation)))
 
@@ -257,25 +268,34 @@ class Segmenter:
         outputs = []
         for lo in range(0, len(rows), self.max_batch):
             chunk = rows[lo:lo + self.max_batch]
-            host = torch.zeros((len(chunk), max_length), dtype=torch.float32).pin_memory()
+            # pinned staging (torch's caching host allocator makes these cheap after the first call)
+            host = torch.empty((len(chunk), max_length), dtype=torch.float32, pin_memory=True)
             for i, r in enumerate(chunk):
-                host[i, :r.shape[-1]] = r.to(torch.float32)
+                n = r.shape[-1]
+                host[i, :n].copy_(r)
+                if n < max_length:
+                    host[i, n:].zero_()
             n_host = torch.tensor(lengths[lo:lo + len(chunk)], dtype=torch.int32).pin_memory()
             wav_dev = host.to(eng.device, non_blocking=True)
             n_dev = n_host.to(eng.device, non_blocking=True)
             hidden, seg, cnt, feat = eng.forward(wav_dev, n_dev, np.float32(self.norm_threshold),
                                                  np.float32(self.merge_threshold))
-            cnt_h = cnt.cpu().numpy()
-            hidden_h = hidden.cpu().numpy()
-            n_max = int(cnt_h.max()) if len(cnt_h) else 0
-            seg_h = seg[:, :max(n_max, 1)].cpu().numpy()
-            feat_h = feat[:, :max(n_max, 1)].cpu().numpy()
+            hidden_pin = torch.empty(hidden.shape, dtype=torch.float32, pin_memory=True)
+            hidden_pin.copy_(hidden, non_blocking=True)
+            cnt_h = cnt.cpu().numpy()                      # synchronises the stream
+            n_max = max(int(cnt_h.max()) if len(cnt_h) else 0, 1)
+            seg_pin = torch.empty((len(chunk), n_max, 2), dtype=torch.int32, pin_memory=True)
+            feat_pin = torch.empty((len(chunk), n_max, HIDDEN), dtype=torch.float32, pin_memory=True)
+            seg_pin.copy_(seg[:, :n_max], non_blocking=True)
+            feat_pin.copy_(feat[:, :n_max], non_blocking=True)
+            torch.cuda.current_stream(eng.device).synchronize()
+            hidden_h, seg_h, feat_h = hidden_pin.numpy(), seg_pin.numpy(), feat_pin.numpy()
             for i in range(len(chunk)):
                 n = int(cnt_h[i])
                 segments = seg_h[i, :n].astype(np.int64) if n > 0 else np.array([])
                 outputs.append({
                     'segments': segments * 1.0 / FRAME_RATE if in_second else segments,
-                    'segment_features': feat_h[i, :n].copy() if n > 0 else np.array([]),
+                    'segment_features': feat_h[i, :n] if n > 0 else np.array([]),
                     'hidden_states': hidden_h[i],
                 })
         return outputs if is_batch else outputs[0]
