@@ -17,6 +17,7 @@
 #include "attention.cuh"
 #include "frontend.cuh"
 #include "gemm_tc.cuh"
+#include "posconv.cuh"
 #include "segment.cuh"
 
 using namespace syl;
@@ -63,9 +64,9 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// fp16 tensor map, up to 3 dims, 128B swizzle, box = {64, box1, 1}
-bool make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
-                   uint32_t box1, std::string* err) {
+// tiled tensor map of up to 3 dims; elem_bytes 2 (fp16) or 4 (fp32); swizzle_bytes 128 or 64; box = {box0, box1, 1}
+bool make_tmap(CUtensorMap* map, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+               const uint64_t* strides_elems, uint32_t box0, uint32_t box1, int swizzle_bytes, std::string* err) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     *err = "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)";
@@ -73,22 +74,37 @@ bool make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t*
   }
   cuuint64_t gdim[3] = {1, 1, 1};
   cuuint64_t gstr[2] = {0, 0};
-  cuuint32_t box[3] = {64, box1, 1};
+  cuuint32_t box[3] = {box0, box1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   for (int i = 0; i < rank; ++i) gdim[i] = dims[i];
-  for (int i = 1; i < rank; ++i) gstr[i - 1] = strides_elems[i] * 2;
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, box,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  for (int i = 1; i < rank; ++i) gstr[i - 1] = strides_elems[i] * (uint64_t)elem_bytes;
+  CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                  const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
-    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu strides %llu %llu box1 %u",
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu strides %llu %llu box %u %u",
              (int)r, rank, (unsigned long long)gdim[0], (unsigned long long)gdim[1], (unsigned long long)gdim[2],
-             (unsigned long long)gstr[0], (unsigned long long)gstr[1], box1);
+             (unsigned long long)gstr[0], (unsigned long long)gstr[1], box0, box1);
     *err = buf;
     return false;
   }
   return true;
+}
+
+// fp16 operand map: 128B swizzle, box = {64, box1, 1}
+bool make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                   uint32_t box1, std::string* err) {
+  return make_tmap(map, base, 2, rank, dims, strides_elems, 64, box1, 128, err);
+}
+
+// output maps over a channels-last [batches][rows][ld] tensor: fp32 box {32,32} swizzle 128B, fp16 box {32,32} swizzle 64B
+bool make_out_map(CUtensorMap* map, const void* base, int elem_bytes, int ld, int rows_per_batch, int batches,
+                  std::string* err) {
+  uint64_t dims[3] = {(uint64_t)ld, (uint64_t)rows_per_batch, (uint64_t)batches};
+  uint64_t str[3] = {1, (uint64_t)ld, (uint64_t)rows_per_batch * ld};
+  return make_tmap(map, base, elem_bytes, 3, dims, str, 32, 32, elem_bytes == 4 ? 128 : 64, err);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -160,6 +176,10 @@ __global__ void pack_pos_w_kernel(const float* __restrict__ v, const float* __re
   }
 }
 
+__global__ void add_inplace_kernel(float* __restrict__ x, const float* __restrict__ y, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] += y[i];
+}
+
 __global__ void valid_frames_kernel(const int32_t* __restrict__ n_samples, int batch, int T, int32_t* __restrict__ valid) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
@@ -204,9 +224,14 @@ struct LayerW {
 
 struct GemmOp {
   CUtensorMap a_hi, a_lo;
+  CUtensorMap o_f32, o_hi, o_lo;
   const PackedLinear* w = nullptr;
   GemmParams p;
-  int block_n = 256;
+};
+
+struct PosOp {
+  CUtensorMap a_hi, a_lo, o_map;
+  PosConvParams p;
 };
 
 struct WsLayout {
@@ -225,9 +250,10 @@ struct Plan {
   float* hidden = nullptr;
   WsLayout lay;
   GemmOp conv[6];
-  GemmOp proj, pos;
+  GemmOp proj;
+  PosOp pos;
   std::vector<GemmOp> qkv, out, ffn1, ffn2;   // per layer (A maps are shared, params differ in weights)
-  CUtensorMap attn_map;
+  CUtensorMap attn_map, ctx_hi_map, ctx_lo_map;
 };
 
 }  // namespace
@@ -431,52 +457,76 @@ GemmParams base_params() {
   return p;
 }
 
-// plain [M,K] row-major A operand
-bool make_plain_a(syl_handle* h, GemmOp& op, const __half* hi, const __half* lo, int M, int K) {
-  uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, 1};
-  uint64_t str[3] = {1, (uint64_t)K, (uint64_t)M * K};
+// A operand over a [batches][rows][K] fp16 tensor (plain matrices use batches = 1)
+bool make_a_maps(syl_handle* h, GemmOp& op, const __half* hi, const __half* lo, int K, int rows, int batches,
+                 uint64_t row_stride, uint64_t batch_stride) {
+  uint64_t dims[3] = {(uint64_t)K, (uint64_t)rows, (uint64_t)batches};
+  uint64_t str[3] = {1, row_stride, batch_stride};
   if (!make_tmap_f16(&op.a_hi, hi, 3, dims, str, 128, &h->err)) return false;
   if (!make_tmap_f16(&op.a_lo, lo ? lo : hi, 3, dims, str, 128, &h->err)) return false;
-  op.p.rows_per_batch = M;
-  op.p.batches = 1;
+  op.p.rows_per_batch = rows;
+  op.p.batches = batches;
   op.p.kb_per_pass = K / GEMM_BLOCK_K;
-  op.p.kb_per_tap = K / GEMM_BLOCK_K;
-  op.p.tap_row_step = 0;
-  op.p.row_offset = 0;
-  op.p.a_col_per_ntile = 0;
   return true;
 }
 
-int launch_gemm(syl_handle* h, const GemmOp& op, cudaStream_t st, int sm_count) {
+// output maps; any of the three destinations may be null
+bool make_o_maps(syl_handle* h, GemmOp& op, float* f32, __half* hi, __half* lo, int ld) {
+  memset(&op.o_f32, 0, sizeof(CUtensorMap));
+  memset(&op.o_hi, 0, sizeof(CUtensorMap));
+  memset(&op.o_lo, 0, sizeof(CUtensorMap));
+  const int rows = op.p.rows_per_batch, nb = op.p.batches;
+  if (f32 && !make_out_map(&op.o_f32, f32, 4, ld, rows, nb, &h->err)) return false;
+  if (hi && !make_out_map(&op.o_hi, hi, 2, ld, rows, nb, &h->err)) return false;
+  if (lo && !make_out_map(&op.o_lo, lo, 2, ld, rows, nb, &h->err)) return false;
+  op.p.out_f32 = f32 != nullptr;
+  op.p.out_hi = hi != nullptr;
+  op.p.out_lo = lo != nullptr;
+  return true;
+}
+
+int launch_gemm_raw(const GemmOp& op, const CUtensorMap& b_hi, const CUtensorMap& b_lo, cudaStream_t st, int sm_count) {
   const GemmParams& p = op.p;
   const int tiles_m = p.batches * ((p.rows_per_batch + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M);
-  const int tiles = tiles_m * (p.N / op.block_n);
+  const int tiles = tiles_m * (p.N / GEMM_BLOCK_N);
   const int grid = std::min(tiles, sm_count);
   if (grid <= 0) return SYL_OK;
-  if (op.block_n == 256) {
-    gemm_tc_kernel<256><<<grid, GEMM_THREADS, GemmSmem<256>::kTotal, st>>>(op.a_hi, op.a_lo, op.w->map_hi, op.w->map_lo, p);
-  } else if (op.block_n == 48) {
-    gemm_tc_kernel<48><<<grid, GEMM_THREADS, GemmSmem<48>::kTotal, st>>>(op.a_hi, op.a_lo, op.w->map_hi, op.w->map_lo, p);
-  } else {
-    return fail(h, SYL_E_ARG, "unsupported block_n %d", op.block_n);
-  }
-  CUDA_TRY(h, cudaGetLastError());
+  gemm_tc_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_TOTAL, st>>>(op.a_hi, op.a_lo, b_hi, b_lo, op.o_f32, op.o_hi, op.o_lo, p);
+  return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
+}
+
+int launch_gemm(syl_handle* h, const GemmOp& op, cudaStream_t st, int sm_count) {
+  if (launch_gemm_raw(op, op.w->map_hi, op.w->map_lo, st, sm_count) != SYL_OK)
+    return fail(h, SYL_E_CUDA, "gemm launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   return SYL_OK;
 }
 
-int set_kernel_attrs(syl_handle* h) {
-  CUDA_TRY(h, cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<256>::kTotal));
-  CUDA_TRY(h, cudaFuncSetAttribute(gemm_tc_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<48>::kTotal));
-  CUDA_TRY(h, cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
+int launch_posconv(syl_handle* h, const PosOp& op, cudaStream_t st, int sm_count) {
+  const int t_tiles = (op.p.T + PC_TILE_T - 1) / PC_TILE_T;
+  const int tiles = op.p.batches * t_tiles * PC_GROUPS;
+  posconv_kernel<<<std::min(tiles, sm_count), PC_THREADS, PC_SMEM_TOTAL, st>>>(op.a_hi, op.a_lo, h->pos.map_hi, h->pos.map_lo,
+                                                                             op.o_map, op.p);
+  CUDA_TRY(h, cudaGetLastError());
   return SYL_OK;
 }
 
 bool g_attrs_set = false;
 int ensure_attrs(syl_handle* h) {
   if (g_attrs_set) return SYL_OK;
-  int rc = set_kernel_attrs(h);
-  if (rc == SYL_OK) g_attrs_set = true;
-  return rc;
+  CUDA_TRY(h, cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_TOTAL));
+  CUDA_TRY(h, cudaFuncSetAttribute(posconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM_TOTAL));
+  CUDA_TRY(h, cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
+  g_attrs_set = true;
+  return SYL_OK;
+}
+
+int posconv_base_offset_mode() {
+  // Measured on B200 (profiles/r01_posconv_base_offset.md): the UMMA swizzle XOR is a function of the absolute
+  // shared-memory address, exactly like TMA's, so a descriptor whose start is shifted by whole 128-byte rows needs
+  // base_offset = 0.  Setting (addr >> 7) & 7 there produces wrong results.  The env var only exists to re-run
+  // that experiment.
+  const char* e = getenv("SYL_POSCONV_BASE_OFFSET");
+  return e ? atoi(e) : 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -501,74 +551,46 @@ int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
     GemmOp& op = pl.conv[i - 1];
     op.p = base_params();
     op.w = &h->convw[i - 1];
-    op.block_n = 256;
     const int k = kConvK[i], s = kConvS[i], Lin = L.L[i - 1], Lout = L.L[i];
-    uint64_t dims[3] = {(uint64_t)k * kC, (uint64_t)Lout, (uint64_t)batch};
-    uint64_t str[3] = {1, (uint64_t)s * kC, (uint64_t)Lin * kC};
-    if (!make_tmap_f16(&op.a_hi, at<__half>(ws, L.act_hi[i - 1]), 3, dims, str, 128, &h->err)) return SYL_E_CUDA;
-    if (!make_tmap_f16(&op.a_lo, at<__half>(ws, L.act_lo[i - 1]), 3, dims, str, 128, &h->err)) return SYL_E_CUDA;
-    op.p.rows_per_batch = Lout;
-    op.p.batches = batch;
+    if (!make_a_maps(h, op, at<__half>(ws, L.act_hi[i - 1]), at<__half>(ws, L.act_lo[i - 1]), k * kC, Lout, batch,
+                     (uint64_t)s * kC, (uint64_t)Lin * kC))
+      return SYL_E_CUDA;
     op.p.N = kC;
-    op.p.kb_per_pass = k * kC / GEMM_BLOCK_K;
-    op.p.kb_per_tap = op.p.kb_per_pass;
     op.p.n_pass = split_conv ? 3 : 1;
     op.p.act = 1;
-    op.p.ldo = kC;
-    if (i < 6) {
-      op.p.out_hi = at<__half>(ws, L.act_hi[i]);
-      op.p.out_lo = split_conv ? at<__half>(ws, L.act_lo[i]) : nullptr;
-    } else {
-      op.p.out_f32 = at<float>(ws, L.conv6);
-    }
+    const bool ok = (i < 6) ? make_o_maps(h, op, nullptr, at<__half>(ws, L.act_hi[i]),
+                                          split_conv ? at<__half>(ws, L.act_lo[i]) : nullptr, kC)
+                            : make_o_maps(h, op, at<float>(ws, L.conv6), nullptr, nullptr, kC);
+    if (!ok) return SYL_E_CUDA;
   }
-  // feature projection: LN(512) output -> 768, bias, zero padded frames (modeling_hubert.py:229, :429-432)
+  // feature projection: LN(512) output -> 768, bias, zero padded frames (modeling_hubert.py:229, :429-432);
+  // tiled per utterance so that valid_rows indexes the batch
   {
     GemmOp& op = pl.proj;
     op.p = base_params();
     op.w = &h->proj;
-    op.block_n = 256;
-    if (!make_plain_a(h, op, at<__half>(ws, L.ln_hi), at<__half>(ws, L.ln_lo), M, kC)) return SYL_E_CUDA;
-    op.p.rows_per_batch = T;   // per-utterance tiles so that valid_rows indexes the batch
-    op.p.batches = batch;
-    {
-      uint64_t dims[3] = {(uint64_t)kC, (uint64_t)T, (uint64_t)batch};
-      uint64_t str[3] = {1, (uint64_t)kC, (uint64_t)T * kC};
-      if (!make_tmap_f16(&op.a_hi, at<__half>(ws, L.ln_hi), 3, dims, str, 128, &h->err)) return SYL_E_CUDA;
-      if (!make_tmap_f16(&op.a_lo, at<__half>(ws, L.ln_lo), 3, dims, str, 128, &h->err)) return SYL_E_CUDA;
-    }
+    if (!make_a_maps(h, op, at<__half>(ws, L.ln_hi), at<__half>(ws, L.ln_lo), kC, T, batch, kC, (uint64_t)T * kC))
+      return SYL_E_CUDA;
     op.p.N = kH;
     op.p.n_pass = split_proj ? 3 : 1;
     op.p.bias = h->proj.bias;
     op.p.valid_rows = at<int32_t>(ws, L.valid);
-    op.p.out_f32 = at<float>(ws, L.h);
-    op.p.out_hi = at<__half>(ws, L.h16_hi);
-    op.p.out_lo = split_proj ? at<__half>(ws, L.h16_lo) : nullptr;
-    op.p.ldo = kH;
+    if (!make_o_maps(h, op, at<float>(ws, L.h), at<__half>(ws, L.h16_hi), split_proj ? at<__half>(ws, L.h16_lo) : nullptr, kH))
+      return SYL_E_CUDA;
   }
-  // positional conv: 16 groups x (48 -> 48), 128 taps; K loop over taps, A rows shift by one frame per tap
+  // positional conv (posconv.cuh): activation window resident in smem, weights stream per tap
   {
-    GemmOp& op = pl.pos;
-    op.p = base_params();
-    op.w = &h->pos;
-    op.block_n = 48;
+    PosOp& op = pl.pos;
     uint64_t dims[3] = {(uint64_t)kH, (uint64_t)T, (uint64_t)batch};
     uint64_t str[3] = {1, (uint64_t)kH, (uint64_t)T * kH};
-    if (!make_tmap_f16(&op.a_hi, at<__half>(ws, L.h16_hi), 3, dims, str, 128, &h->err)) return SYL_E_CUDA;
-    if (!make_tmap_f16(&op.a_lo, at<__half>(ws, L.h16_lo), 3, dims, str, 128, &h->err)) return SYL_E_CUDA;
-    op.p.rows_per_batch = T;
+    if (!make_tmap_f16(&op.a_hi, at<__half>(ws, L.h16_hi), 3, dims, str, PC_WIN_ROWS / 2, &h->err)) return SYL_E_CUDA;
+    if (!make_tmap_f16(&op.a_lo, at<__half>(ws, L.h16_lo), 3, dims, str, PC_WIN_ROWS / 2, &h->err)) return SYL_E_CUDA;
+    if (!make_tmap(&op.o_map, at<float>(ws, L.pos), 4, 3, dims, str, 16, 32, 64, &h->err)) return SYL_E_CUDA;
+    op.p.T = T;
     op.p.batches = batch;
-    op.p.N = kH;
-    op.p.kb_per_pass = kPosK;
-    op.p.kb_per_tap = 1;
-    op.p.tap_row_step = 1;
-    op.p.row_offset = -(kPosK / 2);
-    op.p.a_col_per_ntile = kPosCg;
     op.p.n_pass = split_proj ? 3 : 1;
     op.p.bias = h->pos.bias;
-    op.p.act = 1;
-    op.p.out_f32 = at<float>(ws, L.pos);
-    op.p.ldo = kH;
+    op.p.use_base_offset = posconv_base_offset_mode();
   }
   // encoder layers
   const int nl = h->n_layers;
@@ -582,57 +604,54 @@ int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
       GemmOp& op = pl.qkv[l];
       op.p = base_params();
       op.w = &w.qkv;
-      if (!make_plain_a(h, op, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), M, kH)) return SYL_E_CUDA;
+      if (!make_a_maps(h, op, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), kH, M, 1, kH, (uint64_t)M * kH)) return SYL_E_CUDA;
       op.p.N = 3 * kH;
       op.p.n_pass = split_enc ? 3 : 1;
       op.p.bias = w.qkv.bias;
       op.p.col_scale = 0.125f;        // head_dim ** -0.5, exact (modeling_hubert.py:287)
       op.p.col_scale_limit = kH;
-      op.p.out_hi = at<__half>(ws, L.qkv);
-      op.p.ldo = 3 * kH;
+      if (!make_o_maps(h, op, nullptr, at<__half>(ws, L.qkv), nullptr, 3 * kH)) return SYL_E_CUDA;
     }
     {
       GemmOp& op = pl.out[l];
       op.p = base_params();
       op.w = &w.out;
-      if (!make_plain_a(h, op, at<__half>(ws, L.ctx_hi), at<__half>(ws, L.ctx_lo), M, kH)) return SYL_E_CUDA;
+      if (!make_a_maps(h, op, at<__half>(ws, L.ctx_hi), at<__half>(ws, L.ctx_lo), kH, M, 1, kH, (uint64_t)M * kH)) return SYL_E_CUDA;
       op.p.N = kH;
       op.p.n_pass = split_enc ? 3 : 1;
       op.p.bias = w.out.bias;
-      op.p.residual = at<float>(ws, L.h);
-      op.p.out_f32 = at<float>(ws, L.pre);
-      op.p.ldo = kH;
+      if (!make_o_maps(h, op, at<float>(ws, L.pre), nullptr, nullptr, kH)) return SYL_E_CUDA;
     }
     {
       GemmOp& op = pl.ffn1[l];
       op.p = base_params();
       op.w = &w.ffn1;
-      if (!make_plain_a(h, op, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), M, kH)) return SYL_E_CUDA;
+      if (!make_a_maps(h, op, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), kH, M, 1, kH, (uint64_t)M * kH)) return SYL_E_CUDA;
       op.p.N = kF;
       op.p.n_pass = split_enc ? 3 : 1;
       op.p.bias = w.ffn1.bias;
       op.p.act = 1;
-      op.p.out_hi = at<__half>(ws, L.mid_hi);
-      op.p.out_lo = split_enc ? at<__half>(ws, L.mid_lo) : nullptr;
-      op.p.ldo = kF;
+      if (!make_o_maps(h, op, nullptr, at<__half>(ws, L.mid_hi), split_enc ? at<__half>(ws, L.mid_lo) : nullptr, kF)) return SYL_E_CUDA;
     }
     {
       GemmOp& op = pl.ffn2[l];
       op.p = base_params();
       op.w = &w.ffn2;
-      if (!make_plain_a(h, op, at<__half>(ws, L.mid_hi), at<__half>(ws, L.mid_lo), M, kF)) return SYL_E_CUDA;
+      if (!make_a_maps(h, op, at<__half>(ws, L.mid_hi), at<__half>(ws, L.mid_lo), kF, M, 1, kF, (uint64_t)M * kF)) return SYL_E_CUDA;
       op.p.N = kH;
       op.p.n_pass = split_enc ? 3 : 1;
       op.p.bias = w.ffn2.bias;
-      op.p.residual = at<float>(ws, L.h);
-      op.p.out_f32 = at<float>(ws, L.pre);
-      op.p.ldo = kH;
+      if (!make_o_maps(h, op, at<float>(ws, L.pre), nullptr, nullptr, kH)) return SYL_E_CUDA;
     }
   }
   {
     uint64_t dims[3] = {(uint64_t)3 * kH, (uint64_t)T, (uint64_t)batch};
     uint64_t str[3] = {1, (uint64_t)3 * kH, (uint64_t)T * 3 * kH};
     if (!make_tmap_f16(&pl.attn_map, at<__half>(ws, L.qkv), 3, dims, str, 128, &h->err)) return SYL_E_CUDA;
+    uint64_t od[3] = {(uint64_t)kH, (uint64_t)T, (uint64_t)batch};
+    uint64_t os[3] = {1, (uint64_t)kH, (uint64_t)T * kH};
+    if (!make_tmap(&pl.ctx_hi_map, at<__half>(ws, L.ctx_hi), 2, 3, od, os, 64, 32, 128, &h->err)) return SYL_E_CUDA;
+    if (!make_tmap(&pl.ctx_lo_map, at<__half>(ws, L.ctx_lo), 2, 3, od, os, 64, 32, 128, &h->err)) return SYL_E_CUDA;
   }
   pl.valid = true;
   return SYL_OK;
@@ -645,21 +664,36 @@ void launch_ln(const float* x, const float* add, const float* g, const float* b,
   layernorm_rows_kernel<D><<<(rows + warps - 1) / warps, warps * 32, 0, st>>>(x, add, g, b, rows, of, ohi, olo);
 }
 
+int launch_attention(const CUtensorMap& qkv, const CUtensorMap& o_hi, const CUtensorMap& o_lo, const int32_t* kv_len,
+                     int B, int T, int out_lo, int sm_count, cudaStream_t st) {
+  AttnParams ap;
+  ap.T = T;
+  ap.batches = B;
+  ap.heads = kHeads;
+  ap.model_dim = kH;
+  ap.kv_len = kv_len;
+  ap.out_lo = out_lo;
+  const int q_tiles = (T + ATT_BQ - 1) / ATT_BQ;
+  const int items = B * kHeads * ((q_tiles + 1) / 2);
+  attention_kernel<<<std::min(items, sm_count), ATT_THREADS, ATT_SMEM_TOTAL, st>>>(qkv, o_hi, o_lo, ap);
+  return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
+}
+
 int run_frontend(syl_handle* h, const float* wav, cudaStream_t st) {
   Plan& pl = h->plan;
   const WsLayout& L = pl.lay;
   void* ws = pl.ws;
   const int B = pl.batch, L0 = L.L[0];
   {
-  StageTimer tm(h, ST_CONV0, st);
-  CUDA_TRY(h, cudaMemsetAsync(at<double>(ws, L.mom), 0, (size_t)B * C0_NMOM * sizeof(double), st));
-  conv0_moments_kernel<<<dim3((L0 + MOM_T_PER_BLOCK - 1) / MOM_T_PER_BLOCK, B), MOM_THREADS, 0, st>>>(
-      wav, pl.t_samp, L0, at<double>(ws, L.mom));
-  conv0_gn_coeff_kernel<<<B, kC, 0, st>>>(at<double>(ws, L.mom), h->conv0_w, h->gn_g, h->gn_b, L0,
-                                          at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift));
-  conv0_apply_kernel<<<dim3((L0 + C0A_T - 1) / C0A_T, B), C0A_THREADS, 0, st>>>(
-      wav, pl.t_samp, L0, h->conv0_w, at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift),
-      at<__half>(ws, L.act_hi[0]), (h->mode & SYL_SPLIT_CONV) ? at<__half>(ws, L.act_lo[0]) : nullptr);
+    StageTimer tm(h, ST_CONV0, st);
+    CUDA_TRY(h, cudaMemsetAsync(at<double>(ws, L.mom), 0, (size_t)B * C0_NMOM * sizeof(double), st));
+    conv0_moments_kernel<<<dim3((L0 + MOM_T_PER_BLOCK - 1) / MOM_T_PER_BLOCK, B), MOM_THREADS, 0, st>>>(
+        wav, pl.t_samp, L0, at<double>(ws, L.mom));
+    conv0_gn_coeff_kernel<<<B, kC, 0, st>>>(at<double>(ws, L.mom), h->conv0_w, h->gn_g, h->gn_b, L0,
+                                            at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift));
+    conv0_apply_kernel<<<dim3((L0 + C0A_T - 1) / C0A_T, B), C0A_THREADS, 0, st>>>(
+        wav, pl.t_samp, L0, h->conv0_w, at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift),
+        at<__half>(ws, L.act_hi[0]), (h->mode & SYL_SPLIT_CONV) ? at<__half>(ws, L.act_lo[0]) : nullptr);
   }
   CUDA_TRY(h, cudaGetLastError());
   StageTimer tm(h, ST_CONV, st);
@@ -670,6 +704,7 @@ int run_frontend(syl_handle* h, const float* wav, cudaStream_t st) {
   return SYL_OK;
 }
 
+// one post-LN encoder layer (modeling_hubert.py:388-405); residual adds are fused into the LayerNorm kernels
 int run_layer(syl_handle* h, int l, float* h_out, cudaStream_t st) {
   Plan& pl = h->plan;
   const WsLayout& L = pl.lay;
@@ -682,25 +717,18 @@ int run_layer(syl_handle* h, int l, float* h_out, cudaStream_t st) {
     StageTimer tm(h, ST_QKV, st);
     if ((rc = launch_gemm(h, pl.qkv[l], st, h->sm_count))) return rc;
   }
-  AttnParams ap;
-  ap.T = T;
-  ap.heads = kHeads;
-  ap.model_dim = kH;
-  ap.kv_len = at<int32_t>(ws, L.valid);
-  ap.out_hi = at<__half>(ws, L.ctx_hi);
-  ap.out_lo = split_enc ? at<__half>(ws, L.ctx_lo) : nullptr;
   {
     StageTimer tm(h, ST_ATTN, st);
-    attention_kernel<<<dim3((T + ATT_BQ - 1) / ATT_BQ, kHeads, B), ATT_THREADS, ATT_SMEM_TOTAL, st>>>(pl.attn_map, ap);
+    if (launch_attention(pl.attn_map, pl.ctx_hi_map, pl.ctx_lo_map, at<int32_t>(ws, L.valid), B, T, split_enc, h->sm_count, st))
+      return fail(h, SYL_E_CUDA, "attention launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
-  CUDA_TRY(h, cudaGetLastError());
   {
     StageTimer tm(h, ST_OUT, st);
     if ((rc = launch_gemm(h, pl.out[l], st, h->sm_count))) return rc;
   }
   {
-    StageTimer tm(h, ST_LN, st);
-    launch_ln<kH>(at<float>(ws, L.pre), nullptr, w.ln1_g, w.ln1_b, M, at<float>(ws, L.h), at<__half>(ws, L.h16_hi),
+    StageTimer tm(h, ST_LN, st);   // h = LN(h + attn)
+    launch_ln<kH>(at<float>(ws, L.pre), at<float>(ws, L.h), w.ln1_g, w.ln1_b, M, at<float>(ws, L.h), at<__half>(ws, L.h16_hi),
                   split_enc ? at<__half>(ws, L.h16_lo) : nullptr, st);
   }
   {
@@ -712,8 +740,8 @@ int run_layer(syl_handle* h, int l, float* h_out, cudaStream_t st) {
     if ((rc = launch_gemm(h, pl.ffn2[l], st, h->sm_count))) return rc;
   }
   {
-    StageTimer tm(h, ST_LN, st);
-    launch_ln<kH>(at<float>(ws, L.pre), nullptr, w.ln2_g, w.ln2_b, M, h_out, at<__half>(ws, L.h16_hi),
+    StageTimer tm(h, ST_LN, st);   // h = LN(h + ffn)
+    launch_ln<kH>(at<float>(ws, L.pre), at<float>(ws, L.h), w.ln2_g, w.ln2_b, M, h_out, at<__half>(ws, L.h16_hi),
                   split_enc ? at<__half>(ws, L.h16_lo) : nullptr, st);
   }
   CUDA_TRY(h, cudaGetLastError());
@@ -922,7 +950,7 @@ int syl_forward(syl_handle* h, const float* wav, const int32_t* n_samples, int b
   }
   {
     StageTimer tm(h, ST_POS, st);
-    if ((rc = launch_gemm(h, pl.pos, st, h->sm_count))) return rc;
+    if ((rc = launch_posconv(h, pl.pos, st, h->sm_count))) return rc;
   }
   const int nl = (h->active_layers >= 0 && h->active_layers < h->n_layers) ? h->active_layers : h->n_layers;
   // h = LN(h + pos)   (modeling_hubert.py:441-442); with zero layers this is already the output
@@ -992,27 +1020,23 @@ int syl_encoder_layer(syl_handle* h, int layer, const float* h_in, const int32_t
 }
 
 int syl_attention(const void* qkv_f16, const int32_t* kv_len, int batch, int T, void* out_f16, void* stream) {
-  static std::string err;
-  if (!qkv_f16 || !out_f16 || batch <= 0 || T <= 0) return SYL_E_ARG;
+  std::string err;
+  if (!qkv_f16 || !out_f16 || batch <= 0 || T <= 0) return fail(nullptr, SYL_E_ARG, "syl_attention: bad arguments");
   if (cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL) != cudaSuccess)
-    return SYL_E_CUDA;
-  CUtensorMap map;
+    return fail(nullptr, SYL_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
+  CUtensorMap map, omap;
   uint64_t dims[3] = {(uint64_t)3 * kH, (uint64_t)T, (uint64_t)batch};
   uint64_t str[3] = {1, (uint64_t)3 * kH, (uint64_t)T * 3 * kH};
-  if (!make_tmap_f16(&map, qkv_f16, 3, dims, str, 128, &err)) {
-    g_create_error = err;
-    return SYL_E_CUDA;
-  }
-  AttnParams ap;
-  ap.T = T;
-  ap.heads = kHeads;
-  ap.model_dim = kH;
-  ap.kv_len = kv_len;
-  ap.out_hi = reinterpret_cast<__half*>(out_f16);
-  ap.out_lo = nullptr;
-  attention_kernel<<<dim3((T + ATT_BQ - 1) / ATT_BQ, kHeads, batch), ATT_THREADS, ATT_SMEM_TOTAL,
-                     reinterpret_cast<cudaStream_t>(stream)>>>(map, ap);
-  return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
+  uint64_t od[3] = {(uint64_t)kH, (uint64_t)T, (uint64_t)batch};
+  uint64_t os[3] = {1, (uint64_t)kH, (uint64_t)T * kH};
+  if (!make_tmap_f16(&map, qkv_f16, 3, dims, str, 128, &err) || !make_tmap(&omap, out_f16, 2, 3, od, os, 64, 32, 128, &err))
+    return fail(nullptr, SYL_E_CUDA, "%s", err.c_str());
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (launch_attention(map, omap, omap, kv_len, batch, T, 0, sms, reinterpret_cast<cudaStream_t>(stream)) != SYL_OK)
+    return fail(nullptr, SYL_E_CUDA, "attention launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return SYL_OK;
 }
 
 size_t syl_segment_workspace_bytes(int batch, int T) {
@@ -1043,7 +1067,7 @@ int syl_gemm_f32(const float* A, const float* W, const float* bias, const float*
   if (N % 256 != 0 || K % 64 != 0) return fail(nullptr, SYL_E_ARG, "syl_gemm_f32: N must be a multiple of 256 and K of 64");
   if (n_pass != 1 && n_pass != 3) return fail(nullptr, SYL_E_ARG, "syl_gemm_f32: n_pass must be 1 or 3");
   if (workspace_bytes < syl_gemm_workspace_bytes(M, N, K)) return fail(nullptr, SYL_E_WORKSPACE, "syl_gemm_f32: workspace too small");
-  if (cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<256>::kTotal) != cudaSuccess)
+  if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_TOTAL) != cudaSuccess)
     return fail(nullptr, SYL_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   auto al = [](size_t b) { return (b + 1023) & ~size_t(1023); };
@@ -1055,39 +1079,32 @@ int syl_gemm_f32(const float* A, const float* W, const float* bias, const float*
   split_f32_kernel<<<grid_for((size_t)M * K), 256, 0, st>>>(A, a_hi, a_lo, (size_t)M * K);
   split_f32_kernel<<<grid_for((size_t)N * K), 256, 0, st>>>(W, w_hi, w_lo, (size_t)N * K);
   std::string err;
-  PackedLinear pw;
-  pw.hi = w_hi;
-  pw.lo = w_lo;
-  pw.N = N;
-  pw.K = K;
+  CUtensorMap b_hi, b_lo;
   uint64_t wd[2] = {(uint64_t)K, (uint64_t)N}, wsd[2] = {1, (uint64_t)K};
-  if (!make_tmap_f16(&pw.map_hi, w_hi, 2, wd, wsd, 256, &err) || !make_tmap_f16(&pw.map_lo, w_lo, 2, wd, wsd, 256, &err))
+  if (!make_tmap_f16(&b_hi, w_hi, 2, wd, wsd, 256, &err) || !make_tmap_f16(&b_lo, w_lo, 2, wd, wsd, 256, &err))
     return fail(nullptr, SYL_E_CUDA, "%s", err.c_str());
   GemmOp op;
   op.p = base_params();
-  op.w = &pw;
-  op.block_n = 256;
   uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, 1}, str[3] = {1, (uint64_t)K, (uint64_t)M * K};
   if (!make_tmap_f16(&op.a_hi, a_hi, 3, dims, str, 128, &err) || !make_tmap_f16(&op.a_lo, a_lo, 3, dims, str, 128, &err))
     return fail(nullptr, SYL_E_CUDA, "%s", err.c_str());
+  memset(&op.o_hi, 0, sizeof(CUtensorMap));
+  memset(&op.o_lo, 0, sizeof(CUtensorMap));
+  if (!make_out_map(&op.o_f32, out, 4, N, M, 1, &err)) return fail(nullptr, SYL_E_CUDA, "%s", err.c_str());
   op.p.rows_per_batch = M;
   op.p.batches = 1;
   op.p.N = N;
   op.p.kb_per_pass = K / GEMM_BLOCK_K;
-  op.p.kb_per_tap = op.p.kb_per_pass;
   op.p.n_pass = n_pass;
   op.p.bias = bias;
-  op.p.residual = residual;
   op.p.act = act;
-  op.p.out_f32 = out;
-  op.p.ldo = N;
+  op.p.out_f32 = 1;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int tiles = ((M + 127) / 128) * (N / 256);
-  gemm_tc_kernel<256><<<std::min(tiles, sms), GEMM_THREADS, GemmSmem<256>::kTotal, st>>>(op.a_hi, op.a_lo, pw.map_hi, pw.map_lo, op.p);
-  if (cudaGetLastError() != cudaSuccess) return fail(nullptr, SYL_E_CUDA, "gemm launch failed");
-  return SYL_OK;
+  if (launch_gemm_raw(op, b_hi, b_lo, st, sms) != SYL_OK) return fail(nullptr, SYL_E_CUDA, "gemm launch failed");
+  if (residual) add_inplace_kernel<<<grid_for((size_t)M * N), 256, 0, st>>>(out, residual, (size_t)M * N);
+  return cudaGetLastError() == cudaSuccess ? SYL_OK : fail(nullptr, SYL_E_CUDA, "launch failed");
 }
 
 int syl_powf_half(const float* x, float* y, int64_t n, void* stream) {
