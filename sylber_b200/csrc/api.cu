@@ -416,7 +416,7 @@ WsLayout make_layout(int batch, int t_samp) {
     return o;
   };
   const size_t B = batch, M = B * w.T;
-  w.mom = take(B * C0_NMOM * sizeof(double));
+  w.mom = take(B * (size_t)((w.L[0] + MOM_T_PER_BLOCK - 1) / MOM_T_PER_BLOCK) * C0_NMOM * sizeof(double));
   w.gn_scale = take(B * kC * sizeof(float));
   w.gn_shift = take(B * kC * sizeof(float));
   w.valid = take(B * sizeof(int32_t));
@@ -686,10 +686,9 @@ int run_frontend(syl_handle* h, const float* wav, cudaStream_t st) {
   const int B = pl.batch, L0 = L.L[0];
   {
     StageTimer tm(h, ST_CONV0, st);
-    CUDA_TRY(h, cudaMemsetAsync(at<double>(ws, L.mom), 0, (size_t)B * C0_NMOM * sizeof(double), st));
-    conv0_moments_kernel<<<dim3((L0 + MOM_T_PER_BLOCK - 1) / MOM_T_PER_BLOCK, B), MOM_THREADS, 0, st>>>(
-        wav, pl.t_samp, L0, at<double>(ws, L.mom));
-    conv0_gn_coeff_kernel<<<B, kC, 0, st>>>(at<double>(ws, L.mom), h->conv0_w, h->gn_g, h->gn_b, L0,
+    const int chunks = (L0 + MOM_T_PER_BLOCK - 1) / MOM_T_PER_BLOCK;
+    conv0_moments_kernel<<<dim3(chunks, B), MOM_THREADS, 0, st>>>(wav, pl.t_samp, L0, at<double>(ws, L.mom));
+    conv0_gn_coeff_kernel<<<B, kC, 0, st>>>(at<double>(ws, L.mom), chunks, h->conv0_w, h->gn_g, h->gn_b, L0,
                                             at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift));
     conv0_apply_kernel<<<dim3((L0 + C0A_T - 1) / C0A_T, B), C0A_THREADS, 0, st>>>(
         wav, pl.t_samp, L0, h->conv0_w, at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift),

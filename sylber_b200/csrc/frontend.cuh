@@ -21,22 +21,22 @@ constexpr int C0_OUT = 512;
 constexpr int C0_NMOM = C0_K + C0_K * (C0_K + 1) / 2;  // 10 sums + 55 upper-triangle second moments
 
 // ----------------------------------------------------------------------------------------------
-// conv0 moments: grid (chunks, B), block 128.  mom[b][65] must be zeroed before the launch.
+// conv0 moments: grid (chunks, B), block 128.  Each block writes its partial sums to part[b][chunk][65]; the
+// coefficient kernel adds the chunks in index order, so the statistics are bit-reproducible run to run.
 // ----------------------------------------------------------------------------------------------
 constexpr int MOM_THREADS = 128;
 constexpr int MOM_T_PER_BLOCK = 1024;
 
 __global__ void __launch_bounds__(MOM_THREADS)
-conv0_moments_kernel(const float* __restrict__ wav, int t_samp, int L0, double* __restrict__ mom) {
+conv0_moments_kernel(const float* __restrict__ wav, int t_samp, int L0, double* __restrict__ part) {
   __shared__ float xs[MOM_T_PER_BLOCK * C0_S + C0_K];
-  __shared__ double red[C0_NMOM];
+  __shared__ double red[MOM_THREADS / 32][C0_NMOM];
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * MOM_T_PER_BLOCK;
   const int nt = min(MOM_T_PER_BLOCK, L0 - t0);
   const float* w = wav + (size_t)b * t_samp + (size_t)t0 * C0_S;
   const int nsamp = nt * C0_S + (C0_K - C0_S);
   for (int i = threadIdx.x; i < nsamp; i += MOM_THREADS) xs[i] = w[i];
-  if (threadIdx.x < C0_NMOM) red[threadIdx.x] = 0.0;
   __syncthreads();
 
   double acc[C0_NMOM];
@@ -59,19 +59,30 @@ conv0_moments_kernel(const float* __restrict__ wav, int t_samp, int L0, double* 
     double v = acc[i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane_id() == 0) atomicAdd(&red[i], v);
+    if (lane_id() == 0) red[threadIdx.x >> 5][i] = v;
   }
   __syncthreads();
-  if (threadIdx.x < C0_NMOM) atomicAdd(&mom[(size_t)b * C0_NMOM + threadIdx.x], red[threadIdx.x]);
+  if (threadIdx.x < C0_NMOM) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < MOM_THREADS / 32; ++w) v += red[w][threadIdx.x];
+    part[((size_t)b * gridDim.x + blockIdx.x) * C0_NMOM + threadIdx.x] = v;
+  }
 }
 
 // per (b, c): GroupNorm scale/shift so that  gn(y) = y * scale + shift   (eps 1e-5, biased variance)
-__global__ void conv0_gn_coeff_kernel(const double* __restrict__ mom, const float* __restrict__ w0,
+__global__ void conv0_gn_coeff_kernel(const double* __restrict__ part, int chunks, const float* __restrict__ w0,
                                       const float* __restrict__ gamma, const float* __restrict__ beta, int L0,
                                       float* __restrict__ scale, float* __restrict__ shift) {
+  __shared__ double m[C0_NMOM];
   const int b = blockIdx.x;
   const int c = threadIdx.x;
-  const double* m = mom + (size_t)b * C0_NMOM;
+  if (c < C0_NMOM) {
+    double v = 0.0;
+    for (int k = 0; k < chunks; ++k) v += part[((size_t)b * chunks + k) * C0_NMOM + c];
+    m[c] = v;
+  }
+  __syncthreads();
   double w[C0_K];
 #pragma unroll
   for (int j = 0; j < C0_K; ++j) w[j] = (double)w0[c * C0_K + j];

@@ -1,0 +1,66 @@
+"""The C-ABI library: builds, loads, exports every function the header declares, and fails loudly without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from sylber_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "sylber_b200.h")
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(syl_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(lib):
+    names = _declared_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    # and the Python binding table covers the whole header
+    assert set(names) == set(_lib.SIGNATURES)
+
+
+def test_pure_host_entry_points(lib):
+    assert lib.syl_num_frames(160000) == 499
+    assert lib.syl_num_frames(46080) == 143
+    assert lib.syl_num_frames(399) == 0
+    assert lib.syl_workspace_bytes(None, 0, 160000) == 0
+    assert lib.syl_workspace_bytes(None, 1, 100) == 0
+    b1 = lib.syl_workspace_bytes(None, 1, 160000)
+    b32 = lib.syl_workspace_bytes(None, 32, 160000)
+    assert 0 < b1 < b32 < 8 * 2 ** 30
+    assert b32 % 1024 == 0
+    assert lib.syl_segment_workspace_bytes(4, 499) > 4 * 499 * 4
+    assert lib.syl_num_stages() == 11
+    assert lib.syl_stage_name(1) == b"conv1_6_gemm"
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_silent_cpu_fallback(lib):
+    h = ctypes.c_void_p()
+    rc = lib.syl_create(ctypes.byref(h), 0, 9, 1)
+    assert rc == -3                                   # SYL_E_CUDA
+    assert b"no CPU fallback" in lib.syl_last_error(None)
+    from sylber_b200 import Segmenter
+    from sylber_b200.weights import random_hubert_state_dict
+    with pytest.raises(RuntimeError):
+        Segmenter(model_ckpt=None, state_dict=random_hubert_state_dict(1), encoding_layer=1, device="cuda")
+    with pytest.raises(RuntimeError):
+        Segmenter(model_ckpt=None, state_dict=random_hubert_state_dict(1), encoding_layer=1, device="cpu")
+
+
+def test_product_does_not_import_oracle():
+    """The shipped package must never route through oracle/ (that would void every parity claim)."""
+    pkg = os.path.join(ROOT, "sylber_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
