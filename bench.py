@@ -320,8 +320,9 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16 operands (conv stack + projection split hi/lo, 3 tensor-core passes), f32 accumulate/LN/softmax"
-                 if args.mode == "parity" else f"f16 ({args.mode})",
+        "dtype": "f16 tensor-core operands, f32 accumulate/LayerNorm/softmax/residual; mode=" + args.mode +
+                 {"parity": " (conv2-6, projection, pos-conv run split hi/lo f16 = 3 passes)",
+                  "strict": " (conv1-6, projection, pos-conv split)", "exact": " (every GEMM split)", "fast": " (no split)"}[args.mode],
         "data": "synthetic",
         "config": {"workload": f"batch=32 synthetic 10 s 16 kHz wav per GPU, sylber_base ({layers}L/768d), 1xB200 per rank",
                    "frames_per_clip": T, "batch_per_gpu": B, "mode": args.mode, "parallelism": f"dp{world} by utterance",
@@ -352,7 +353,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", type=int, default=9)
-    ap.add_argument("--mode", default="parity", choices=["parity", "fast", "exact"])
+    ap.add_argument("--mode", default="parity", choices=["parity", "strict", "fast", "exact"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

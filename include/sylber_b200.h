@@ -39,12 +39,14 @@ typedef struct syl_handle syl_handle;
 
 /* precision mode = bit mask of the GEMM sites that run split precision (fp16 hi + lo operands, 3 tensor-core
  * passes, ~fp32 accuracy) instead of a single fp16 pass.  DESIGN.md explains the measured error budget. */
-#define SYL_SPLIT_CONV 1     /* conv1..conv6 of the feature encoder (dominant error source) */
+#define SYL_SPLIT_CONV 1     /* conv2..conv6 of the feature encoder (dominant error source) */
+#define SYL_SPLIT_CONV1 8    /* conv1, half of the conv stack's FLOPs */
 #define SYL_SPLIT_PROJ 2     /* feature projection + positional conv */
 #define SYL_SPLIT_ENC 4      /* encoder linear layers (QKV, out-proj, FFN) */
-#define SYL_MODE_PARITY (SYL_SPLIT_CONV | SYL_SPLIT_PROJ)    /* default: meets 1e-3 rel vs the fp32 reference */
-#define SYL_MODE_FAST 0                                      /* single-pass fp16 everywhere */
-#define SYL_MODE_EXACT (SYL_SPLIT_CONV | SYL_SPLIT_PROJ | SYL_SPLIT_ENC)
+#define SYL_MODE_PARITY (SYL_SPLIT_CONV | SYL_SPLIT_PROJ)    /* default: 3.6e-4 rel vs the fp32 reference (bar: 1e-3) */
+#define SYL_MODE_STRICT (SYL_SPLIT_CONV | SYL_SPLIT_CONV1 | SYL_SPLIT_PROJ)  /* conv1 split too: 3.0e-4 rel, +18 % time */
+#define SYL_MODE_FAST 0                                      /* single-pass fp16 everywhere: ~5e-4 .. 1e-3 rel */
+#define SYL_MODE_EXACT (SYL_SPLIT_CONV | SYL_SPLIT_CONV1 | SYL_SPLIT_PROJ | SYL_SPLIT_ENC)
 
 #define SYL_DTYPE_F32 0
 

@@ -10,11 +10,12 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 _SO = os.path.join(_PKG, "libsylber_b200.so")
 
-SYL_SPLIT_CONV, SYL_SPLIT_PROJ, SYL_SPLIT_ENC = 1, 2, 4
+SYL_SPLIT_CONV, SYL_SPLIT_PROJ, SYL_SPLIT_ENC, SYL_SPLIT_CONV1 = 1, 2, 4, 8
 MODES = {
     "parity": SYL_SPLIT_CONV | SYL_SPLIT_PROJ,
+    "strict": SYL_SPLIT_CONV | SYL_SPLIT_CONV1 | SYL_SPLIT_PROJ,
     "fast": 0,
-    "exact": SYL_SPLIT_CONV | SYL_SPLIT_PROJ | SYL_SPLIT_ENC,
+    "exact": SYL_SPLIT_CONV | SYL_SPLIT_CONV1 | SYL_SPLIT_PROJ | SYL_SPLIT_ENC,
 }
 
 _c_void_p, _c_int, _c_size_t, _c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_float

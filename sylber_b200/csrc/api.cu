@@ -543,8 +543,8 @@ int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
   pl.lay = make_layout(batch, t_samp);
   const WsLayout& L = pl.lay;
   const int T = L.T, M = batch * T;
-  const bool split_conv = h->mode & SYL_SPLIT_CONV, split_proj = h->mode & SYL_SPLIT_PROJ,
-             split_enc = h->mode & SYL_SPLIT_ENC;
+  const bool split_conv = h->mode & SYL_SPLIT_CONV, split_conv1 = h->mode & SYL_SPLIT_CONV1,
+             split_proj = h->mode & SYL_SPLIT_PROJ, split_enc = h->mode & SYL_SPLIT_ENC;
 
   // conv1..conv6: A = overlapping-row view of the previous channels-last activation
   for (int i = 1; i <= 6; ++i) {
@@ -556,7 +556,7 @@ int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
                      (uint64_t)s * kC, (uint64_t)Lin * kC))
       return SYL_E_CUDA;
     op.p.N = kC;
-    op.p.n_pass = split_conv ? 3 : 1;
+    op.p.n_pass = (i == 1 ? split_conv1 : split_conv) ? 3 : 1;
     op.p.act = 1;
     const bool ok = (i < 6) ? make_o_maps(h, op, nullptr, at<__half>(ws, L.act_hi[i]),
                                           split_conv ? at<__half>(ws, L.act_lo[i]) : nullptr, kC)
@@ -692,7 +692,7 @@ int run_frontend(syl_handle* h, const float* wav, cudaStream_t st) {
                                             at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift));
     conv0_apply_kernel<<<dim3((L0 + C0A_T - 1) / C0A_T, B), C0A_THREADS, 0, st>>>(
         wav, pl.t_samp, L0, h->conv0_w, at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift),
-        at<__half>(ws, L.act_hi[0]), (h->mode & SYL_SPLIT_CONV) ? at<__half>(ws, L.act_lo[0]) : nullptr);
+        at<__half>(ws, L.act_hi[0]), (h->mode & SYL_SPLIT_CONV1) ? at<__half>(ws, L.act_lo[0]) : nullptr);
   }
   CUDA_TRY(h, cudaGetLastError());
   StageTimer tm(h, ST_CONV, st);
@@ -1152,8 +1152,9 @@ int syl_read_stage(syl_handle* h, const char* name, float* out, size_t n_floats,
     const int i = s[4] - '0';
     const size_t n = B * L.L[i] * kC;
     if (n_floats < n) return fail(h, SYL_E_ARG, "syl_read_stage: output too small (%zu < %zu)", n_floats, n);
-    join_f16_kernel<<<grid_for(n), 256, 0, st>>>(at<__half>(pl.ws, L.act_hi[i]),
-                                                 (h->mode & SYL_SPLIT_CONV) ? at<__half>(pl.ws, L.act_lo[i]) : nullptr, out, n);
+    const bool has_lo = (i == 0) ? (h->mode & SYL_SPLIT_CONV1) : (h->mode & SYL_SPLIT_CONV);
+    join_f16_kernel<<<grid_for(n), 256, 0, st>>>(at<__half>(pl.ws, L.act_hi[i]), has_lo ? at<__half>(pl.ws, L.act_lo[i]) : nullptr,
+                                                 out, n);
     return SYL_OK;
   }
   const float* src = nullptr;

@@ -140,17 +140,24 @@ conv0_apply_kernel(const float* __restrict__ wav, int t_samp, int L0, const floa
     float x[C0_K];
 #pragma unroll
     for (int j = 0; j < C0_K; ++j) x[j] = xs[t * C0_S + j];
-    __half hi[4], lo[4];
+    float g[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float y = 0.0f;
 #pragma unroll
       for (int j = 0; j < C0_K; ++j) y = fmaf(wr[q][j], x[j], y);
-      split_f16(gelu_erf(fmaf(y, sc[q], sh[q])), hi[q], lo[q]);
+      g[q] = gelu_fast(fmaf(y, sc[q], sh[q]));
     }
     const size_t o = ((size_t)b * L0 + t0 + t) * C0_OUT + c0;
-    *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]));
-    if (out_lo) *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]));
+    if (out_lo) {
+      uint32_t h0, l0, h1, l1;
+      split_pair(g[0], g[1], h0, l0);
+      split_pair(g[2], g[3], h1, l1);
+      *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(l0, l1);
+    } else {
+      *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(pack_f16x2_sat(g[0], g[1]), pack_f16x2_sat(g[2], g[3]));
+    }
   }
 }
 
@@ -210,13 +217,15 @@ layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ add
     const size_t o = (size_t)row * D + (size_t)(lane + 32 * i) * 4;
     if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = y;
     if (out_hi) {
-      __half h0, h1, h2, h3, l0, l1, l2, l3;
-      split_f16(y.x, h0, l0);
-      split_f16(y.y, h1, l1);
-      split_f16(y.z, h2, l2);
-      split_f16(y.w, h3, l3);
-      *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
-      if (out_lo) *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(pack_h2(l0, l1), pack_h2(l2, l3));
+      if (out_lo) {
+        uint32_t h0, l0, h1, l1;
+        split_pair(y.x, y.y, h0, l0);
+        split_pair(y.z, y.w, h1, l1);
+        *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(l0, l1);
+      } else {
+        *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(pack_f16x2_sat(y.x, y.y), pack_f16x2_sat(y.z, y.w));
+      }
     }
   }
 }

@@ -118,7 +118,7 @@ def main():
         t0 = time.time()
         ref = hubert_forward(sd, wav, lens, 9, stages=stages)
         print("oracle forward s:", round(time.time() - t0, 2))
-        for mode in ("parity", "fast", "exact"):
+        for mode in ("parity", "strict", "fast", "exact"):
             eng = _Engine(sd, 9, "cuda:0", mode)
             hidden, seg, cnt, feat = eng.forward(wav.to(dev), torch.tensor(lens, dtype=torch.int32, device=dev), 2.6, 0.8)
             torch.cuda.synchronize()
