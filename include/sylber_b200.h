@@ -105,6 +105,10 @@ int syl_set_active_layers(syl_handle* h, int n);
 /* how many kernels of this library syl_forward launches for the given shape (bench.py reports it) */
 int syl_forward_launch_count(const syl_handle* h, int with_segmentation);
 
+/* syl_forward replays the whole launch sequence as one CUDA graph when it is called again with the same argument
+ * set (default on; off = always launch eagerly).  Profiling (below) always uses the eager path. */
+int syl_set_graph_mode(syl_handle* h, int on);
+
 /* per-stage device timing: when enabled, syl_forward brackets each stage with CUDA events on the launch stream.
  * syl_profile_read waits for the recorded events, returns the accumulated milliseconds and region counts per
  * stage since the previous read (arrays of syl_num_stages() entries) and resets the accumulation. */

@@ -45,6 +45,7 @@ SIGNATURES = {
     "syl_read_stage": (_c_int, [_c_void_p, ctypes.c_char_p, _c_void_p, _c_size_t, _c_void_p]),
     "syl_set_active_layers": (_c_int, [_c_void_p, _c_int]),
     "syl_forward_launch_count": (_c_int, [_c_void_p, _c_int]),
+    "syl_set_graph_mode": (_c_int, [_c_void_p, _c_int]),
     "syl_num_stages": (_c_int, []),
     "syl_stage_name": (ctypes.c_char_p, [_c_int]),
     "syl_profile_enable": (_c_int, [_c_void_p, _c_int]),

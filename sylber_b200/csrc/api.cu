@@ -254,6 +254,14 @@ struct Plan {
   PosOp pos;
   std::vector<GemmOp> qkv, out, ffn1, ffn2;   // per layer (A maps are shared, params differ in weights)
   CUtensorMap attn_map, ctx_hi_map, ctx_lo_map;
+  // CUDA graphs of the whole forward, one per distinct argument set (pointers + thresholds)
+  struct GraphEntry {
+    const void* key[6];
+    int max_seg, active_layers;
+    float thr_norm, thr_merge;
+    cudaGraphExec_t exec;
+  };
+  std::vector<GraphEntry> graphs;
 };
 
 }  // namespace
@@ -276,9 +284,12 @@ struct syl_handle {
   PackedLinear pos;
   float *enc_ln_g = nullptr, *enc_ln_b = nullptr;
   std::vector<LayerW> layers;
-  Plan plan;
+  Plan plans[4];       // small cache: callers that alternate between workspaces (sub-batch streams) keep their maps
+  int plan_cur = 0;
+  int plan_next = 0;
   int sm_count = 148;
   bool profile = false;
+  bool use_graphs = true;
   std::vector<ProfRec> recs;
   std::vector<cudaEvent_t> pool;
   size_t pool_used = 0;
@@ -533,9 +544,19 @@ int posconv_base_offset_mode() {
 // plan: tensor maps + GEMM parameters for one (batch, t_samp, workspace, hidden) combination
 // ------------------------------------------------------------------------------------------------
 int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
-  Plan& pl = h->plan;
-  if (pl.valid && pl.batch == batch && pl.t_samp == t_samp && pl.ws == ws && pl.hidden == hidden) return SYL_OK;
+  for (int i = 0; i < 4; ++i) {
+    const Plan& c = h->plans[i];
+    if (c.valid && c.batch == batch && c.t_samp == t_samp && c.ws == ws) {
+      h->plan_cur = i;
+      return SYL_OK;
+    }
+  }
+  h->plan_cur = h->plan_next;
+  h->plan_next = (h->plan_next + 1) % 4;
+  Plan& pl = h->plans[h->plan_cur];
   pl.valid = false;
+  for (auto& g : pl.graphs) cudaGraphExecDestroy(g.exec);
+  pl.graphs.clear();
   pl.batch = batch;
   pl.t_samp = t_samp;
   pl.ws = ws;
@@ -680,7 +701,7 @@ int launch_attention(const CUtensorMap& qkv, const CUtensorMap& o_hi, const CUte
 }
 
 int run_frontend(syl_handle* h, const float* wav, cudaStream_t st) {
-  Plan& pl = h->plan;
+  Plan& pl = h->plans[h->plan_cur];
   const WsLayout& L = pl.lay;
   void* ws = pl.ws;
   const int B = pl.batch, L0 = L.L[0];
@@ -705,7 +726,7 @@ int run_frontend(syl_handle* h, const float* wav, cudaStream_t st) {
 
 // one post-LN encoder layer (modeling_hubert.py:388-405); residual adds are fused into the LayerNorm kernels
 int run_layer(syl_handle* h, int l, float* h_out, cudaStream_t st) {
-  Plan& pl = h->plan;
+  Plan& pl = h->plans[h->plan_cur];
   const WsLayout& L = pl.lay;
   void* ws = pl.ws;
   const int B = pl.batch, T = L.T, M = B * T;
@@ -798,6 +819,8 @@ void syl_destroy(syl_handle* h) {
   for (auto& kv : h->raw) cudaFree(kv.second.first);
   for (void* p : h->owned) cudaFree(p);
   for (cudaEvent_t e : h->pool) cudaEventDestroy(e);
+  for (Plan& pl : h->plans)
+    for (auto& g : pl.graphs) cudaGraphExecDestroy(g.exec);
   delete h;
 }
 
@@ -913,26 +936,16 @@ int syl_forward_launch_count(const syl_handle* h, int with_segmentation) {
   return 4 + 6 + 4 + nl * 7 + (with_segmentation ? 3 : 0);
 }
 
-int syl_forward(syl_handle* h, const float* wav, const int32_t* n_samples, int batch, int t_samp_max, float* hidden,
-                int32_t* seg, int32_t* seg_count, float* seg_feat, int max_seg, float thr_norm, float thr_merge,
-                void* workspace, size_t workspace_bytes, void* stream) {
-  if (!h) return SYL_E_ARG;
-  if (!h->finalized) return fail(h, SYL_E_STATE, "syl_forward before syl_finalize");
-  if (!wav || !hidden || !workspace || batch <= 0) return fail(h, SYL_E_ARG, "syl_forward: null pointer or empty batch");
-  if (t_samp_max < 400) return fail(h, SYL_E_ARG, "syl_forward: need at least 400 samples (one frame), got %d", t_samp_max);
-  const size_t need = syl_workspace_bytes(h, batch, t_samp_max);
-  if (workspace_bytes < need) return fail(h, SYL_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
-  if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return fail(h, SYL_E_ARG, "workspace must be 1024-byte aligned");
-  if (seg && (!seg_count || max_seg <= 0)) return fail(h, SYL_E_ARG, "syl_forward: seg needs seg_count and max_seg > 0");
-  CUDA_TRY(h, cudaSetDevice(h->device));
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  int rc = build_plan(h, batch, t_samp_max, workspace, hidden);
-  if (rc) return rc;
-  Plan& pl = h->plan;
+// enqueue every kernel of one forward on `st` (eagerly, or into a stream capture)
+static int enqueue_forward(syl_handle* h, Plan& pl, const float* wav, const int32_t* n_samples, float* hidden,
+                           int32_t* seg, int32_t* seg_count, float* seg_feat, int max_seg, float thr_norm,
+                           float thr_merge, cudaStream_t st) {
   const WsLayout& L = pl.lay;
+  void* workspace = pl.ws;
+  const int batch = pl.batch;
   const int T = L.T, M = batch * T;
   const bool split_proj = h->mode & SYL_SPLIT_PROJ, split_enc = h->mode & SYL_SPLIT_ENC;
-
+  int rc;
   if (n_samples)
     valid_frames_kernel<<<(batch + 127) / 128, 128, 0, st>>>(n_samples, batch, T, at<int32_t>(workspace, L.valid));
   else
@@ -974,6 +987,73 @@ int syl_forward(syl_handle* h, const float* wav, const int32_t* n_samples, int b
   return SYL_OK;
 }
 
+int syl_forward(syl_handle* h, const float* wav, const int32_t* n_samples, int batch, int t_samp_max, float* hidden,
+                int32_t* seg, int32_t* seg_count, float* seg_feat, int max_seg, float thr_norm, float thr_merge,
+                void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return SYL_E_ARG;
+  if (!h->finalized) return fail(h, SYL_E_STATE, "syl_forward before syl_finalize");
+  if (!wav || !hidden || !workspace || batch <= 0) return fail(h, SYL_E_ARG, "syl_forward: null pointer or empty batch");
+  if (t_samp_max < 400) return fail(h, SYL_E_ARG, "syl_forward: need at least 400 samples (one frame), got %d", t_samp_max);
+  const size_t need = syl_workspace_bytes(h, batch, t_samp_max);
+  if (workspace_bytes < need) return fail(h, SYL_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
+  if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return fail(h, SYL_E_ARG, "workspace must be 1024-byte aligned");
+  if (seg && (!seg_count || max_seg <= 0)) return fail(h, SYL_E_ARG, "syl_forward: seg needs seg_count and max_seg > 0");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = build_plan(h, batch, t_samp_max, workspace, hidden);
+  if (rc) return rc;
+  Plan& pl = h->plans[h->plan_cur];
+
+  // The forward is ~80 launches of fixed shape; replaying it as one CUDA graph removes the per-launch host cost
+  // (2.8 ms of CPU per step, measured) and the launch gaps between the short kernels.  Graphs are keyed by the
+  // full argument set; per-stage profiling needs real events, so it uses the eager path.
+  // (the legacy default stream cannot be captured)
+  const bool graphs = h->use_graphs && !h->profile && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
+  if (graphs) {
+    for (const Plan::GraphEntry& g : pl.graphs) {
+      if (g.key[0] == wav && g.key[1] == n_samples && g.key[2] == hidden && g.key[3] == seg && g.key[4] == seg_count &&
+          g.key[5] == seg_feat && g.max_seg == max_seg && g.thr_norm == thr_norm && g.thr_merge == thr_merge &&
+          g.active_layers == h->active_layers) {
+        CUDA_TRY(h, cudaGraphLaunch(g.exec, st));
+        return SYL_OK;
+      }
+    }
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) cudaGetLastError();
+    const bool began = cs == cudaStreamCaptureStatusNone && cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (!began) cudaGetLastError();   // not capturable: clear the error, launch eagerly below
+    if (began) {
+      rc = enqueue_forward(h, pl, wav, n_samples, hidden, seg, seg_count, seg_feat, max_seg, thr_norm, thr_merge, st);
+      cudaGraph_t graph = nullptr;
+      cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      if (rc == SYL_OK && ce == cudaSuccess && graph) {
+        cudaGraphExec_t exec = nullptr;
+        if (cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+          cudaGraphDestroy(graph);
+          if (pl.graphs.size() >= 8) {
+            cudaGraphExecDestroy(pl.graphs.front().exec);
+            pl.graphs.erase(pl.graphs.begin());
+          }
+          Plan::GraphEntry e{{wav, n_samples, hidden, seg, seg_count, seg_feat}, max_seg, h->active_layers, thr_norm, thr_merge, exec};
+          pl.graphs.push_back(e);
+          CUDA_TRY(h, cudaGraphLaunch(exec, st));
+          return SYL_OK;
+        }
+      }
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();   // capture failed: clear the error and fall through to the eager path
+      if (rc != SYL_OK) return rc;
+    }
+  }
+  return enqueue_forward(h, pl, wav, n_samples, hidden, seg, seg_count, seg_feat, max_seg, thr_norm, thr_merge, st);
+}
+
+int syl_set_graph_mode(syl_handle* h, int on) {
+  if (!h) return SYL_E_ARG;
+  h->use_graphs = on != 0;
+  return SYL_OK;
+}
+
 int syl_conv_frontend(syl_handle* h, const float* wav, int batch, int t_samp_max, float* feats, void* workspace,
                       size_t workspace_bytes, void* stream) {
   if (!h) return SYL_E_ARG;
@@ -986,7 +1066,7 @@ int syl_conv_frontend(syl_handle* h, const float* wav, int batch, int t_samp_max
   int rc = build_plan(h, batch, t_samp_max, workspace, nullptr);
   if (rc) return rc;
   if ((rc = run_frontend(h, wav, st))) return rc;
-  const WsLayout& L = h->plan.lay;
+  const WsLayout& L = h->plans[h->plan_cur].lay;
   CUDA_TRY(h, cudaMemcpyAsync(feats, at<float>(workspace, L.conv6), (size_t)batch * L.T * kC * sizeof(float),
                               cudaMemcpyDeviceToDevice, st));
   return SYL_OK;
@@ -1007,7 +1087,7 @@ int syl_encoder_layer(syl_handle* h, int layer, const float* h_in, const int32_t
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int rc = build_plan(h, batch, n, workspace, nullptr);
   if (rc) return rc;
-  const WsLayout& L = h->plan.lay;
+  const WsLayout& L = h->plans[h->plan_cur].lay;
   const size_t M = (size_t)batch * T;
   if (valid_frames)
     CUDA_TRY(h, cudaMemcpyAsync(at<int32_t>(workspace, L.valid), valid_frames, batch * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
@@ -1142,8 +1222,8 @@ int syl_profile_read(syl_handle* h, float* ms, int* counts) {
 
 int syl_read_stage(syl_handle* h, const char* name, float* out, size_t n_floats, void* stream) {
   if (!h || !name || !out) return SYL_E_ARG;
-  if (!h->plan.valid) return fail(h, SYL_E_STATE, "syl_read_stage: no forward has run yet");
-  const Plan& pl = h->plan;
+  if (!h->plans[h->plan_cur].valid) return fail(h, SYL_E_STATE, "syl_read_stage: no forward has run yet");
+  const Plan& pl = h->plans[h->plan_cur];
   const WsLayout& L = pl.lay;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const std::string s(name);

@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import weakref
 from pathlib import Path
 from types import SimpleNamespace
 
@@ -24,6 +25,37 @@ FRAME_RATE = 50
 
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+class _PinnedPool:
+    """Pinned host buffers for results.  cudaHostAlloc costs ~3 ms per call for the 49 MB hidden-state block
+    (measured, tools/e2e_breakdown.py), so blocks are recycled - but only once nothing outside the pool can still
+    see them: every array handed to the caller is a NumPy view whose base chain ends in one root ndarray per
+    block, the pool keeps only a weak reference to that root, and a block is reused when the root has died."""
+
+    def __init__(self):
+        self._blocks = []          # [tensor, weakref-to-root-ndarray or None]
+
+    def _make(self, n_bytes):
+        return torch.empty(max(int(n_bytes), 1), dtype=torch.uint8, pin_memory=True)
+
+    def array(self, shape, dtype=np.float32):
+        """A NumPy array of `shape` backed by pinned memory, plus the torch view to copy into."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        slot = None
+        for ent in self._blocks:
+            if ent[0].numel() >= n and (ent[1] is None or ent[1]() is None):
+                slot = ent
+                break
+        if slot is None:
+            self._blocks = [e for e in self._blocks if e[1] is not None and e[1]() is not None][-6:]   # drop idle blocks
+            slot = [self._make(n), None]
+            self._blocks.append(slot)
+        root = slot[0].numpy()
+        slot[1] = weakref.ref(root)
+        arr = root[:n].view(dtype).reshape(shape)
+        ten = slot[0][:n].view(torch.from_numpy(np.empty(0, dtype)).dtype).view(*shape)
+        return arr, ten
 
 
 class _Engine:
@@ -44,7 +76,11 @@ class _Engine:
         rc = self.lib.syl_create(ctypes.byref(handle), self.index, n_layers, self.mode)
         _lib.check(self.lib, None, rc, "syl_create")
         self.handle = handle
-        self._workspace = None
+        self._workspaces = {}
+        self._io = {}
+        self._stage_in = {}
+        self._streams = []
+        self.pool = _PinnedPool()
         missing = [k for k in REQUIRED_KEYS(n_layers) if k not in state_dict]
         if missing:
             raise RuntimeError(f"checkpoint is missing {len(missing)} tensors, first: {missing[:4]}")
@@ -69,33 +105,70 @@ class _Engine:
     def num_frames(self, n_samples):
         return int(self.lib.syl_num_frames(int(n_samples)))
 
-    def workspace(self, batch, t_samp):
+    def workspace(self, batch, t_samp, slot=0):
+        """Device workspace for one in-flight forward; `slot` separates concurrent sub-batches."""
         need = int(self.lib.syl_workspace_bytes(self.handle, batch, t_samp))
         if need == 0:
             raise ValueError(f"invalid shape batch={batch} samples={t_samp} (need >= 400 samples)")
-        if self._workspace is None or self._workspace.numel() < need:
-            self._workspace = None
-            self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
-        return self._workspace, need
+        ws = self._workspaces.get(slot)
+        if ws is None or ws.numel() < need:
+            self._workspaces[slot] = None
+            ws = self._workspaces[slot] = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return ws, need
 
-    def forward(self, wav, n_samples, thr_norm, thr_merge, segment=True, max_seg=None):
+    def side_streams(self, n):
+        while len(self._streams) < n:
+            self._streams.append(torch.cuda.Stream(device=self.device))
+        return self._streams[:n]
+
+    def stage_input(self, rows, max_length, slot=0):
+        """Zero-padded (B, max_length) fp32 batch in a persistent pinned buffer (consumed within the call)."""
+        B = len(rows)
+        n = B * max_length
+        buf = self._stage_in.get(slot)
+        if buf is None or buf.numel() < n:
+            buf = self._stage_in[slot] = torch.empty(n, dtype=torch.float32, pin_memory=True)
+        host = buf[:n].view(B, max_length)
+        for i, r in enumerate(rows):
+            k = r.shape[-1]
+            host[i, :k].copy_(r)
+            if k < max_length:
+                host[i, k:].zero_()
+        return host
+
+    def device_input(self, slot, B, n):
+        """Persistent device-side (B, n) fp32 batch and (B,) int32 length buffers for one slot."""
+        buf = self._stage_in.get(("dev", slot))
+        if buf is None or buf[0].numel() < B * n or buf[1].numel() < B:
+            buf = self._stage_in[("dev", slot)] = (torch.empty(B * n, dtype=torch.float32, device=self.device),
+                                                   torch.empty(max(B, 64), dtype=torch.int32, device=self.device))
+        return buf[0][:B * n].view(B, n), buf[1][:B]
+
+    def forward(self, wav, n_samples, thr_norm, thr_merge, segment=True, max_seg=None, slot=0):
         """wav (B, T_samp) fp32 cuda, n_samples (B,) int32 cuda or None.
 
         Returns hidden (B,T,768) and, if `segment`, (seg (B,max_seg,2) int32, seg_count (B,) int32,
         seg_feat (B,max_seg,768) fp32), all device tensors on the current stream."""
         B, t_samp = wav.shape
         T = self.num_frames(t_samp)
-        ws, need = self.workspace(B, t_samp)
-        hidden = torch.empty((B, T, HIDDEN), dtype=torch.float32, device=self.device)
-        seg = cnt = feat = None
-        if segment:
-            max_seg = T if max_seg is None else int(max_seg)
-            seg = torch.empty((B, max_seg, 2), dtype=torch.int32, device=self.device)
-            cnt = torch.empty((B,), dtype=torch.int32, device=self.device)
-            feat = torch.empty((B, max_seg, HIDDEN), dtype=torch.float32, device=self.device)
+        ws, need = self.workspace(B, t_samp, slot)
+        max_seg = (T if max_seg is None else int(max_seg)) if segment else 0
+        # Output buffers are persistent per slot: stable pointers let the library replay its CUDA graph.
+        # They are overwritten by the next forward on the same slot - callers that keep results clone them.
+        key = (slot, B, T, max_seg)
+        io = self._io.get(slot)
+        if io is None or io[0] != key:
+            hidden = torch.empty((B, T, HIDDEN), dtype=torch.float32, device=self.device)
+            seg = cnt = feat = None
+            if segment:
+                seg = torch.empty((B, max_seg, 2), dtype=torch.int32, device=self.device)
+                cnt = torch.empty((B,), dtype=torch.int32, device=self.device)
+                feat = torch.empty((B, max_seg, HIDDEN), dtype=torch.float32, device=self.device)
+            io = self._io[slot] = (key, hidden, seg, cnt, feat)
+        _, hidden, seg, cnt, feat = io
         stream = torch.cuda.current_stream(self.device).cuda_stream
         rc = self.lib.syl_forward(self.handle, _ptr(wav), _ptr(n_samples), B, t_samp, _ptr(hidden), _ptr(seg), _ptr(cnt),
-                                  _ptr(feat), max_seg if segment else 0, float(thr_norm), float(thr_merge),
+                                  _ptr(feat), max_seg, float(thr_norm), float(thr_merge),
                                   _ptr(ws), need, ctypes.c_void_p(stream))
         _lib.check(self.lib, self.handle, rc, "syl_forward")
         return hidden, seg, cnt, feat
@@ -150,8 +223,14 @@ class SpeechModel:
         n = None
         if attention_mask is not None:
             n = attention_mask.to(eng.device).sum(-1).to(torch.int32).contiguous()
-        hidden, _, _, _ = eng.forward(wav, n, 0.0, 0.0, segment=False)
-        return SimpleNamespace(last_hidden_state=hidden)
+        main = torch.cuda.current_stream(eng.device)
+        side = eng.side_streams(1)[0]
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            hidden, _, _, _ = eng.forward(wav, n, 0.0, 0.0, segment=False, slot="speech_model")
+            out = hidden.clone()
+        main.wait_stream(side)
+        return SimpleNamespace(last_hidden_state=out)
 
     forward = __call__
 
@@ -190,7 +269,8 @@ class Segmenter:
         (the reference's fallback at :56-58 runs after `.to(device)` has already raised).
       * missing checkpoint tensors raise (the reference's strict=False at :52 ignores them).
       * extra keyword arguments: `state_dict=` (use these tensors instead of loading `model_ckpt`),
-        `mode=` ("parity" default | "fast" | "exact", see include/sylber_b200.h), `max_batch=`.
+        `mode=` ("parity" default | "strict" | "fast" | "exact", see include/sylber_b200.h), `max_batch=`,
+        `streams=` (sub-batches in flight, default 2: copies of one overlap kernels of the other).
     """
 
     def __init__(self,
@@ -205,6 +285,7 @@ class Segmenter:
         state_dict = kwargs.pop("state_dict", None)
         mode = kwargs.pop("mode", "parity")
         self.max_batch = int(kwargs.pop("max_batch", 64))
+        self.streams = int(kwargs.pop("streams", 2))
         self.enc_dim = HIDDEN
         self.encoding_layer = encoding_layer
         self.ema_decay = ema_decay
@@ -265,32 +346,51 @@ class Segmenter:
             rows.extend(w[i] for i in range(w.shape[0]))      # torch.cat(dim=0) at sylber.py:117: channels become rows
         lengths = [int(r.shape[-1]) for r in rows]
         max_length = max(lengths)
+        # Sub-batches run on separate streams so that one sub-batch's host->device / device->host copies overlap the
+        # other's kernels.  Every sub-batch is padded to the batch-wide max_length: results depend on T_max (8a).
+        n_rows = len(rows)
+        n_sub = max(1, min(self.streams, n_rows // 8)) if n_rows <= self.max_batch else 1
+        bounds = []
+        for lo in range(0, n_rows, self.max_batch):
+            hi = min(lo + self.max_batch, n_rows)
+            step = -(-(hi - lo) // n_sub)
+            bounds += [(a, min(a + step, hi)) for a in range(lo, hi, step)]
+        # always a side stream, even for one sub-batch: the legacy default stream cannot be graph-captured
+        streams = eng.side_streams(n_sub)
+        main = torch.cuda.current_stream(eng.device)
+        thr_n, thr_m = np.float32(self.norm_threshold), np.float32(self.merge_threshold)
+        pending = []
+        for k, (lo, hi) in enumerate(bounds):
+            slot = k % len(streams)
+            st = streams[slot]
+            chunk = rows[lo:hi]
+            if k >= len(streams):                      # this slot's staging buffer and workspace are about to be reused
+                st.synchronize()
+            host = eng.stage_input(chunk, max_length, slot)
+            n_host = torch.tensor(lengths[lo:hi], dtype=torch.int32)
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                wav_dev, n_dev = eng.device_input(slot, hi - lo, max_length)
+                wav_dev.copy_(host, non_blocking=True)
+                n_dev.copy_(n_host, non_blocking=True)
+                hidden, seg, cnt, feat = eng.forward(wav_dev, n_dev, thr_n, thr_m, slot=slot)
+                hidden_h, hidden_pin = eng.pool.array(tuple(hidden.shape))
+                hidden_pin.copy_(hidden, non_blocking=True)
+                cnt_pin = torch.empty(cnt.shape, dtype=torch.int32, pin_memory=True)
+                cnt_pin.copy_(cnt, non_blocking=True)
+            pending.append((st, lo, hi, hidden_h, hidden_pin, seg, cnt_pin, feat))
         outputs = []
-        for lo in range(0, len(rows), self.max_batch):
-            chunk = rows[lo:lo + self.max_batch]
-            # pinned staging (torch's caching host allocator makes these cheap after the first call)
-            host = torch.empty((len(chunk), max_length), dtype=torch.float32, pin_memory=True)
-            for i, r in enumerate(chunk):
-                n = r.shape[-1]
-                host[i, :n].copy_(r)
-                if n < max_length:
-                    host[i, n:].zero_()
-            n_host = torch.tensor(lengths[lo:lo + len(chunk)], dtype=torch.int32).pin_memory()
-            wav_dev = host.to(eng.device, non_blocking=True)
-            n_dev = n_host.to(eng.device, non_blocking=True)
-            hidden, seg, cnt, feat = eng.forward(wav_dev, n_dev, np.float32(self.norm_threshold),
-                                                 np.float32(self.merge_threshold))
-            hidden_pin = torch.empty(hidden.shape, dtype=torch.float32, pin_memory=True)
-            hidden_pin.copy_(hidden, non_blocking=True)
-            cnt_h = cnt.cpu().numpy()                      # synchronises the stream
+        for st, lo, hi, hidden_h, hidden_pin, seg, cnt_pin, feat in pending:
+            st.synchronize()
+            cnt_h = cnt_pin.numpy()
             n_max = max(int(cnt_h.max()) if len(cnt_h) else 0, 1)
-            seg_pin = torch.empty((len(chunk), n_max, 2), dtype=torch.int32, pin_memory=True)
-            feat_pin = torch.empty((len(chunk), n_max, HIDDEN), dtype=torch.float32, pin_memory=True)
-            seg_pin.copy_(seg[:, :n_max], non_blocking=True)
-            feat_pin.copy_(feat[:, :n_max], non_blocking=True)
-            torch.cuda.current_stream(eng.device).synchronize()
-            hidden_h, seg_h, feat_h = hidden_pin.numpy(), seg_pin.numpy(), feat_pin.numpy()
-            for i in range(len(chunk)):
+            with torch.cuda.stream(st):
+                seg_h = seg[:, :n_max].cpu().numpy()
+                feat_h, feat_pin = eng.pool.array((hi - lo, n_max, HIDDEN))
+                feat_pin.copy_(feat[:, :n_max], non_blocking=True)
+            st.synchronize()
+            del hidden_pin, feat_pin
+            for i in range(hi - lo):
                 n = int(cnt_h[i])
                 segments = seg_h[i, :n].astype(np.int64) if n > 0 else np.array([])
                 outputs.append({
@@ -298,4 +398,5 @@ class Segmenter:
                     'segment_features': feat_h[i, :n] if n > 0 else np.array([]),
                     'hidden_states': hidden_h[i],
                 })
+        main.wait_stream(streams[0])
         return outputs if is_batch else outputs[0]
