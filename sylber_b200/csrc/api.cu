@@ -17,6 +17,7 @@
 #include "attention.cuh"
 #include "frontend.cuh"
 #include "gemm_tc.cuh"
+#include "gemm2_tc.cuh"
 #include "posconv.cuh"
 #include "segment.cuh"
 
@@ -214,7 +215,8 @@ struct PackedLinear {   // B operand [N][K] fp16 hi/lo + tensor maps + fp32 bias
   __half* lo = nullptr;
   float* bias = nullptr;
   int N = 0, K = 0;
-  CUtensorMap map_hi, map_lo;
+  CUtensorMap map_hi, map_lo;       // box {64, 256}: whole B tile (1-CTA GEMM) / {64, 48} for the positional conv
+  CUtensorMap map2_hi, map2_lo;     // box {64, 128}: one CTA's half of the B tile (2-CTA GEMM)
 };
 
 struct LayerW {
@@ -365,7 +367,9 @@ bool make_weight_maps(syl_handle* h, PackedLinear& w, int block_n) {
   uint64_t dims[2] = {(uint64_t)w.K, (uint64_t)w.N};
   uint64_t str[2] = {1, (uint64_t)w.K};
   return make_tmap_f16(&w.map_hi, w.hi, 2, dims, str, block_n, &h->err) &&
-         make_tmap_f16(&w.map_lo, w.lo, 2, dims, str, block_n, &h->err);
+         make_tmap_f16(&w.map_lo, w.lo, 2, dims, str, block_n, &h->err) &&
+         make_tmap_f16(&w.map2_hi, w.hi, 2, dims, str, std::min(block_n, 128), &h->err) &&
+         make_tmap_f16(&w.map2_lo, w.lo, 2, dims, str, std::min(block_n, 128), &h->err);
 }
 
 // pack a torch Linear weight [N][K] (+ bias) ; several sources may be concatenated along N (QKV)
@@ -506,7 +510,32 @@ int launch_gemm_raw(const GemmOp& op, const CUtensorMap& b_hi, const CUtensorMap
   return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
 }
 
+// 2-CTA clusters: 256-row tiles, each CTA of a pair owns 128 rows and half of the B tile
+int launch_gemm2_raw(const GemmOp& op, const CUtensorMap& b_hi, const CUtensorMap& b_lo, cudaStream_t st, int sm_count) {
+  const GemmParams& p = op.p;
+  const int tiles_m = p.batches * ((p.rows_per_batch + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M));
+  const int tiles = tiles_m * (p.N / GEMM_BLOCK_N);
+  const int clusters = std::min(tiles, sm_count / 2);
+  if (clusters <= 0) return SYL_OK;
+  gemm2_tc_kernel<<<2 * clusters, GEMM_THREADS, GEMM2_SMEM_TOTAL, st>>>(op.a_hi, op.a_lo, b_hi, b_lo, op.o_f32, op.o_hi, op.o_lo, p);
+  return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
+}
+
+bool gemm_use_2cta() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SYL_GEMM_2CTA");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+
 int launch_gemm(syl_handle* h, const GemmOp& op, cudaStream_t st, int sm_count) {
+  if (gemm_use_2cta()) {
+    if (launch_gemm2_raw(op, op.w->map2_hi, op.w->map2_lo, st, sm_count) != SYL_OK)
+      return fail(h, SYL_E_CUDA, "gemm2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return SYL_OK;
+  }
   if (launch_gemm_raw(op, op.w->map_hi, op.w->map_lo, st, sm_count) != SYL_OK)
     return fail(h, SYL_E_CUDA, "gemm launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   return SYL_OK;
@@ -525,6 +554,7 @@ bool g_attrs_set = false;
 int ensure_attrs(syl_handle* h) {
   if (g_attrs_set) return SYL_OK;
   CUDA_TRY(h, cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_TOTAL));
+  CUDA_TRY(h, cudaFuncSetAttribute(gemm2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL));
   CUDA_TRY(h, cudaFuncSetAttribute(posconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM_TOTAL));
   CUDA_TRY(h, cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
   g_attrs_set = true;
@@ -694,6 +724,10 @@ int launch_attention(const CUtensorMap& qkv, const CUtensorMap& o_hi, const CUte
   ap.model_dim = kH;
   ap.kv_len = kv_len;
   ap.out_lo = out_lo;
+  {
+    const char* e = getenv("SYL_ATTN_DEBUG");
+    ap.debug = e ? atoi(e) : 0;
+  }
   const int q_tiles = (T + ATT_BQ - 1) / ATT_BQ;
   const int items = B * kHeads * ((q_tiles + 1) / 2);
   attention_kernel<<<std::min(items, sm_count), ATT_THREADS, ATT_SMEM_TOTAL, st>>>(qkv, o_hi, o_lo, ap);
@@ -1181,7 +1215,17 @@ int syl_gemm_f32(const float* A, const float* W, const float* bias, const float*
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (launch_gemm_raw(op, b_hi, b_lo, st, sms) != SYL_OK) return fail(nullptr, SYL_E_CUDA, "gemm launch failed");
+  if (gemm_use_2cta()) {
+    if (cudaFuncSetAttribute(gemm2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL) != cudaSuccess)
+      return fail(nullptr, SYL_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
+    CUtensorMap b2_hi, b2_lo;
+    if (!make_tmap_f16(&b2_hi, w_hi, 2, wd, wsd, 128, &err) || !make_tmap_f16(&b2_lo, w_lo, 2, wd, wsd, 128, &err))
+      return fail(nullptr, SYL_E_CUDA, "%s", err.c_str());
+    if (launch_gemm2_raw(op, b2_hi, b2_lo, st, sms) != SYL_OK)
+      return fail(nullptr, SYL_E_CUDA, "gemm2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  } else if (launch_gemm_raw(op, b_hi, b_lo, st, sms) != SYL_OK) {
+    return fail(nullptr, SYL_E_CUDA, "gemm launch failed");
+  }
   if (residual) add_inplace_kernel<<<grid_for((size_t)M * N), 256, 0, st>>>(out, residual, (size_t)M * N);
   return cudaGetLastError() == cudaSuccess ? SYL_OK : fail(nullptr, SYL_E_CUDA, "launch failed");
 }

@@ -33,7 +33,7 @@ constexpr int PC_SMEM_W = 2 * PC_WIN_BYTES;                          // ring: [s
 constexpr int PC_SMEM_EPI = PC_SMEM_W + PC_W_STAGES * 2 * PC_W_BYTES; // 8 warps x 2 KB
 constexpr int PC_SMEM_BAR = PC_SMEM_EPI + 8 * 2048;
 constexpr int PC_SMEM_TOTAL = PC_SMEM_BAR + 256 + 1024;
-constexpr uint32_t PC_TMEM_COLS = 256;     // 2 accumulator stages x (2 M-tiles x 64 columns)
+constexpr uint32_t PC_TMEM_COLS = 512;     // 2 accumulator stages x 2 M-tiles x 128 columns (96 used when split)
 
 struct PosConvParams {
   int T;
@@ -133,7 +133,13 @@ posconv_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
+      // Split precision needs A_hi*W_hi + A_lo*W_hi + A_hi*W_lo.  The single issuing thread, not the tensor core, is
+      // the limit with MMAs this small (N=48: 24 cycles each), so W_hi and W_lo - adjacent in the ring stage - are
+      // consumed as ONE N=96 operand by the A_hi pass: columns 0..47 accumulate A_hi*W_hi (+ A_lo*W_hi from the
+      // second MMA), columns 48..95 accumulate A_hi*W_lo, and the epilogue adds the two halves.  12 MMAs per tap
+      // instead of 18.
       constexpr uint32_t idesc = make_idesc_f16(128, PC_CG, 0, 0, 0);
+      constexpr uint32_t idesc96 = make_idesc_f16(128, 2 * PC_CG, 0, 0, 0);
       const uint32_t win_hi = smem_u32(smem + PC_SMEM_WIN_HI);
       const uint32_t win_lo = smem_u32(smem + PC_SMEM_WIN_LO);
       int stage = 0, acc = 0;
@@ -147,21 +153,21 @@ posconv_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__
           mbar_wait(&w_full[stage], phase);
           tc_fence_after_sync();
           const uint32_t wb = smem_u32(smem + PC_SMEM_W + stage * 2 * PC_W_BYTES);
-          const uint64_t bd_hi = make_desc_k_sw128(wb);
-          const uint64_t bd_lo = make_desc_k_sw128(wb + PC_W_BYTES);
+          const uint64_t bd_hi = make_desc_k_sw128(wb);      // [W_hi ; W_lo]: 96 rows when split, 48 otherwise
 #pragma unroll
           for (int m = 0; m < 2; ++m) {
-            const uint32_t tmem_d = tmem_base + acc * 128 + m * 64;
+            const uint32_t tmem_d = tmem_base + acc * 256 + m * 128;
             const uint32_t roff = (uint32_t)(tap + 128 * m) * 128;
             const uint64_t ad_hi = make_desc_k_sw128_shifted(win_hi + roff, p.use_base_offset);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) umma_f16_ss(tmem_d, ad_hi + 2 * k, bd_hi + 2 * k, idesc, (tap | k) != 0);
             if (split) {
               const uint64_t ad_lo = make_desc_k_sw128_shifted(win_lo + roff, p.use_base_offset);
 #pragma unroll
-              for (int k = 0; k < 3; ++k) umma_f16_ss(tmem_d, ad_lo + 2 * k, bd_hi + 2 * k, idesc, 1);
+              for (int k = 0; k < 3; ++k) umma_f16_ss(tmem_d, ad_hi + 2 * k, bd_hi + 2 * k, idesc96, (tap | k) != 0);
 #pragma unroll
-              for (int k = 0; k < 3; ++k) umma_f16_ss(tmem_d, ad_hi + 2 * k, bd_lo + 2 * k, idesc, 1);
+              for (int k = 0; k < 3; ++k) umma_f16_ss(tmem_d, ad_lo + 2 * k, bd_hi + 2 * k, idesc, 1);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 3; ++k) umma_f16_ss(tmem_d, ad_hi + 2 * k, bd_hi + 2 * k, idesc, (tap | k) != 0);
             }
           }
           umma_commit(&w_empty[stage]);
@@ -198,16 +204,21 @@ posconv_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__
       const bool warp_ok = warp_row0 < p.T;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 128 + m * 64);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + m * 128);
 #pragma unroll 1
       for (int c = 0; c < 3; ++c) {
-        uint32_t r[16];
+        uint32_t r[16], r2[16];
         tmem_ld_32x32b_x16(taddr + c * 16, r);
+        if (split) tmem_ld_32x32b_x16(taddr + PC_CG + c * 16, r2);     // the A_hi * W_lo half
         tmem_ld_wait();
         const int col0 = g * PC_CG + c * 16;
         float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = gelu_fast(__uint_as_float(r[i]) + __ldg(p.bias + col0 + i));
+        for (int i = 0; i < 16; ++i) {
+          float acc_v = __uint_as_float(r[i]);
+          if (split) acc_v += __uint_as_float(r2[i]);
+          v[i] = gelu_fast(acc_v + __ldg(p.bias + col0 + i));
+        }
         if (warp_ok) {
           if (lane == 0) tma_store_wait_read();
           __syncwarp();
