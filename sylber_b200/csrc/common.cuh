@@ -52,6 +52,57 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return x * phi;
 }
 
+// ---- packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): two lanes of fp32 math per instruction -------------------
+struct f32x2 { uint64_t v; };
+__device__ __forceinline__ f32x2 pack2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 p, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p.v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+  return d;
+}
+
+// gelu_fast on a pair: same formula, the polynomial and products run as packed fp32, the two MUFU ops per element
+// stay scalar.  ~11 instructions per element instead of ~19.
+__device__ __forceinline__ void gelu_fast2(float x0, float x1, float& g0, float& g1) {
+  const f32x2 x = pack2(x0, x1);
+  const f32x2 z = mul2(pack2(fabsf(x0), fabsf(x1)), pack2(0.70710678118654752440f, 0.70710678118654752440f));
+  const f32x2 den = fma2(z, pack2(0.3275911f, 0.3275911f), pack2(1.0f, 1.0f));
+  float d0, d1, t0, t1;
+  unpack2(den, d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  const f32x2 t = pack2(t0, t1);
+  f32x2 p = fma2(pack2(1.061405429f, 1.061405429f), t, pack2(-1.453152027f, -1.453152027f));
+  p = fma2(p, t, pack2(1.421413741f, 1.421413741f));
+  p = fma2(p, t, pack2(-0.284496736f, -0.284496736f));
+  p = fma2(p, t, pack2(0.254829592f, 0.254829592f));
+  const f32x2 arg = mul2(mul2(z, z), pack2(-1.4426950408889634f, -1.4426950408889634f));
+  float a0, a1, e0, e1;
+  unpack2(arg, a0, a1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  const f32x2 h = mul2(mul2(p, t), mul2(pack2(e0, e1), pack2(0.5f, 0.5f)));      // 0.5 * erfc(z)
+  float h0, h1;
+  unpack2(h, h0, h1);
+  const f32x2 phi = pack2(x0 >= 0.0f ? 1.0f - h0 : h0, x1 >= 0.0f ? 1.0f - h1 : h1);
+  unpack2(mul2(x, phi), g0, g1);
+}
+
 // two fp32 -> packed fp16x2 (a in the low half), round-to-nearest, saturating to +-65504
 __device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {
   uint32_t r;

@@ -223,7 +223,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__
         }
         if (p.act == 1) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+          for (int i = 0; i < 16; ++i) gelu_fast2(v[2 * i], v[2 * i + 1], v[2 * i], v[2 * i + 1]);
         }
         if (zero_row) {
 #pragma unroll

@@ -217,8 +217,10 @@ posconv_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__
         for (int i = 0; i < 16; ++i) {
           float acc_v = __uint_as_float(r[i]);
           if (split) acc_v += __uint_as_float(r2[i]);
-          v[i] = gelu_fast(acc_v + __ldg(p.bias + col0 + i));
+          v[i] = acc_v + __ldg(p.bias + col0 + i);
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gelu_fast2(v[2 * i], v[2 * i + 1], v[2 * i], v[2 * i + 1]);
         if (warp_ok) {
           if (lane == 0) tma_store_wait_read();
           __syncwarp();
