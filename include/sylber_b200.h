@@ -95,6 +95,9 @@ int syl_segment(const float* states, int batch, int T, float thr_norm, float thr
 size_t syl_gemm_workspace_bytes(int M, int N, int K);
 int syl_gemm_f32(const float* A, const float* W, const float* bias, const float* residual, float* out, int M, int N,
                  int K, int n_pass, int act, void* workspace, size_t workspace_bytes, void* stream);
+/* diagnostic: cycles for `iters` x 4 back-to-back tcgen05.mma (M=128, N=n, K=16) issued by one thread of each of
+ * `ctas` CTAs; writes the elapsed clock64 ticks of CTA 0 to cycles_out_dev (one int64) */
+int syl_mma_probe(int n, int iters, int ctas, void* cycles_out_dev, void* stream);
 /* y[i] = powf(x[i], 0.5f) as glibc computes it (the fp64 replay used by the segmentation kernel) */
 int syl_powf_half(const float* x, float* y, int64_t n, void* stream);
 /* copy an intermediate of the most recent syl_forward / syl_conv_frontend out as fp32.

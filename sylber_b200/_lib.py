@@ -41,6 +41,7 @@ SIGNATURES = {
     "syl_gemm_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
     "syl_gemm_f32": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int,
                               _c_int, _c_void_p, _c_size_t, _c_void_p]),
+    "syl_mma_probe": (_c_int, [_c_int, _c_int, _c_int, _c_void_p, _c_void_p]),
     "syl_powf_half": (_c_int, [_c_void_p, _c_void_p, ctypes.c_int64, _c_void_p]),
     "syl_read_stage": (_c_int, [_c_void_p, ctypes.c_char_p, _c_void_p, _c_size_t, _c_void_p]),
     "syl_set_active_layers": (_c_int, [_c_void_p, _c_int]),

@@ -19,6 +19,7 @@
 #include "gemm_tc.cuh"
 #include "gemm2_tc.cuh"
 #include "posconv.cuh"
+#include "mma_probe.cuh"
 #include "segment.cuh"
 
 using namespace syl;
@@ -729,7 +730,7 @@ int launch_attention(const CUtensorMap& qkv, const CUtensorMap& o_hi, const CUte
     ap.debug = e ? atoi(e) : 0;
   }
   const int q_tiles = (T + ATT_BQ - 1) / ATT_BQ;
-  const int items = B * kHeads * ((q_tiles + 1) / 2);
+  const int items = B * kHeads * ((q_tiles + ATT_QT - 1) / ATT_QT);
   attention_kernel<<<std::min(items, sm_count), ATT_THREADS, ATT_SMEM_TOTAL, st>>>(qkv, o_hi, o_lo, ap);
   return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
 }
@@ -817,6 +818,14 @@ int run_segment(const float* states, int B, int T, float thr_norm, float thr_mer
 }
 
 }  // namespace
+
+template <int N>
+static int run_mma_probe(int iters, int ctas, long long* out_dev, cudaStream_t st) {
+  if (cudaFuncSetAttribute(mma_probe_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 1024 + 64) != cudaSuccess)
+    return SYL_E_CUDA;
+  mma_probe_kernel<N><<<ctas, 128, 65536 + 1024 + 64, st>>>(iters, out_dev);
+  return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
+}
 
 // ================================================================================================
 // exported C ABI
@@ -1233,6 +1242,21 @@ int syl_gemm_f32(const float* A, const float* W, const float* bias, const float*
   }
   if (residual) add_inplace_kernel<<<grid_for((size_t)M * N), 256, 0, st>>>(out, residual, (size_t)M * N);
   return cudaGetLastError() == cudaSuccess ? SYL_OK : fail(nullptr, SYL_E_CUDA, "launch failed");
+}
+
+int syl_mma_probe(int n, int iters, int ctas, void* cycles_out_dev, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  long long* out = reinterpret_cast<long long*>(cycles_out_dev);
+  switch (n) {
+    case 16: return run_mma_probe<16>(iters, ctas, out, st);
+    case 32: return run_mma_probe<32>(iters, ctas, out, st);
+    case 48: return run_mma_probe<48>(iters, ctas, out, st);
+    case 64: return run_mma_probe<64>(iters, ctas, out, st);
+    case 96: return run_mma_probe<96>(iters, ctas, out, st);
+    case 128: return run_mma_probe<128>(iters, ctas, out, st);
+    case 256: return run_mma_probe<256>(iters, ctas, out, st);
+    default: return SYL_E_ARG;
+  }
 }
 
 int syl_powf_half(const float* x, float* y, int64_t n, void* stream) {
