@@ -39,14 +39,24 @@ typedef struct syl_handle syl_handle;
 
 /* precision mode = bit mask of the GEMM sites that run split precision (fp16 hi + lo operands, 3 tensor-core
  * passes, ~fp32 accuracy) instead of a single fp16 pass.  DESIGN.md explains the measured error budget. */
-#define SYL_SPLIT_CONV 1     /* conv2..conv6 of the feature encoder (dominant error source) */
+#define SYL_SPLIT_CONV 1     /* shorthand: conv2..conv6 of the feature encoder (= SYL_SPLIT_CONV2 | ... | SYL_SPLIT_CONV6) */
 #define SYL_SPLIT_CONV1 8    /* conv1, half of the conv stack's FLOPs */
-#define SYL_SPLIT_PROJ 2     /* feature projection + positional conv */
+#define SYL_SPLIT_PROJ 2     /* shorthand: feature projection + positional conv (= SYL_SPLIT_FPROJ | SYL_SPLIT_POS) */
 #define SYL_SPLIT_ENC 4      /* encoder linear layers (QKV, out-proj, FFN) */
-#define SYL_MODE_PARITY (SYL_SPLIT_CONV | SYL_SPLIT_PROJ)    /* default: 3.6e-4 rel vs the fp32 reference (bar: 1e-3) */
-#define SYL_MODE_STRICT (SYL_SPLIT_CONV | SYL_SPLIT_CONV1 | SYL_SPLIT_PROJ)  /* conv1 split too: 3.0e-4 rel, +18 % time */
-#define SYL_MODE_FAST 0                                      /* single-pass fp16 everywhere: ~5e-4 .. 1e-3 rel */
-#define SYL_MODE_EXACT (SYL_SPLIT_CONV | SYL_SPLIT_CONV1 | SYL_SPLIT_PROJ | SYL_SPLIT_ENC)
+#define SYL_SPLIT_CONV2 16   /* individual sites, for error-budget experiments (tests/mode_sweep.py) */
+#define SYL_SPLIT_CONV3 32
+#define SYL_SPLIT_CONV4 64
+#define SYL_SPLIT_CONV5 128
+#define SYL_SPLIT_CONV6 256
+#define SYL_SPLIT_FPROJ 512
+#define SYL_SPLIT_POS 1024
+/* Presets.  Measured on B200 against the fp32 CPU oracle (tests/mode_sweep.py, relative Frobenius error of the final
+ * hidden states, bar 1e-3; device ms per step of the bench workload): fast 5.5e-4 / 4.92 ms, parity 4.4e-4 / 5.23 ms,
+ * conv2-6 + projection 3.7e-4 / 6.08 ms, strict 3.0e-4 / 7.51 ms.  Splitting the positional conv buys 0.04e-4. */
+#define SYL_MODE_PARITY (SYL_SPLIT_CONV4 | SYL_SPLIT_CONV5 | SYL_SPLIT_CONV6 | SYL_SPLIT_FPROJ)   /* default */
+#define SYL_MODE_STRICT (SYL_SPLIT_CONV | SYL_SPLIT_CONV1 | SYL_SPLIT_PROJ)  /* whole front end split */
+#define SYL_MODE_FAST 0                                                      /* single-pass fp16 everywhere */
+#define SYL_MODE_EXACT (SYL_SPLIT_CONV | SYL_SPLIT_CONV1 | SYL_SPLIT_PROJ | SYL_SPLIT_ENC)   /* 2.7e-5 */
 
 #define SYL_DTYPE_F32 0
 
@@ -86,6 +96,10 @@ int syl_encoder_layer(syl_handle* h, int layer, const float* h_in, const int32_t
                       float* h_out, void* workspace, size_t workspace_bytes, void* stream);
 /* attention core: qkv [batch*T, 2304] fp16 (Q pre-scaled by 1/8), out [batch*T, 768] fp16 */
 int syl_attention(const void* qkv_f16, const int32_t* kv_len, int batch, int T, void* out_f16, void* stream);
+/* diagnostic: the same launch with CTA 0 logging clock64 stamps of its MMA thread and softmax warpgroups into
+ * trace_dev[7][trace_cap] (int64 device memory, zero it first); decoded by tools/attn_trace.py */
+int syl_attention_trace(const void* qkv_f16, const int32_t* kv_len, int batch, int T, void* out_f16, void* trace_dev,
+                        int trace_cap, void* stream);
 /* segmentation + pooling on given states [batch, T, 768] fp32; workspace >= syl_segment_workspace_bytes */
 size_t syl_segment_workspace_bytes(int batch, int T);
 int syl_segment(const float* states, int batch, int T, float thr_norm, float thr_merge, int32_t* seg,

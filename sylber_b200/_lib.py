@@ -11,8 +11,10 @@ _CSRC = os.path.join(_PKG, "csrc")
 _SO = os.path.join(_PKG, "libsylber_b200.so")
 
 SYL_SPLIT_CONV, SYL_SPLIT_PROJ, SYL_SPLIT_ENC, SYL_SPLIT_CONV1 = 1, 2, 4, 8
+SYL_SPLIT_CONV2, SYL_SPLIT_CONV3, SYL_SPLIT_CONV4, SYL_SPLIT_CONV5, SYL_SPLIT_CONV6 = 16, 32, 64, 128, 256
+SYL_SPLIT_FPROJ, SYL_SPLIT_POS = 512, 1024
 MODES = {
-    "parity": SYL_SPLIT_CONV | SYL_SPLIT_PROJ,
+    "parity": SYL_SPLIT_CONV4 | SYL_SPLIT_CONV5 | SYL_SPLIT_CONV6 | SYL_SPLIT_FPROJ,
     "strict": SYL_SPLIT_CONV | SYL_SPLIT_CONV1 | SYL_SPLIT_PROJ,
     "fast": 0,
     "exact": SYL_SPLIT_CONV | SYL_SPLIT_CONV1 | SYL_SPLIT_PROJ | SYL_SPLIT_ENC,
@@ -35,6 +37,7 @@ SIGNATURES = {
     "syl_encoder_layer": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p,
                                    _c_size_t, _c_void_p]),
     "syl_attention": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p]),
+    "syl_attention_trace": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_int, _c_void_p]),
     "syl_segment_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
     "syl_segment": (_c_int, [_c_void_p, _c_int, _c_int, _c_float, _c_float, _c_void_p, _c_void_p, _c_void_p, _c_int,
                              _c_void_p, _c_size_t, _c_void_p]),

@@ -300,6 +300,12 @@ struct syl_handle {
 
 namespace {
 
+// does conv layer i (1..6) run split precision?
+bool conv_split(int mode, int i) {
+  static const int bit[7] = {0, SYL_SPLIT_CONV1, SYL_SPLIT_CONV2, SYL_SPLIT_CONV3, SYL_SPLIT_CONV4, SYL_SPLIT_CONV5, SYL_SPLIT_CONV6};
+  return i >= 1 && i <= 6 && (mode & bit[i]) != 0;
+}
+
 int fail(syl_handle* h, int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
@@ -558,6 +564,9 @@ int ensure_attrs(syl_handle* h) {
   CUDA_TRY(h, cudaFuncSetAttribute(gemm2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL));
   CUDA_TRY(h, cudaFuncSetAttribute(posconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM_TOTAL));
   CUDA_TRY(h, cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
+  CUDA_TRY(h, (cudaFuncSetAttribute(attention7_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL)));
+  CUDA_TRY(h, (cudaFuncSetAttribute(attention7_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL)));
+  CUDA_TRY(h, (cudaFuncSetAttribute(attention7_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL)));
   g_attrs_set = true;
   return SYL_OK;
 }
@@ -595,8 +604,7 @@ int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
   pl.lay = make_layout(batch, t_samp);
   const WsLayout& L = pl.lay;
   const int T = L.T, M = batch * T;
-  const bool split_conv = h->mode & SYL_SPLIT_CONV, split_conv1 = h->mode & SYL_SPLIT_CONV1,
-             split_proj = h->mode & SYL_SPLIT_PROJ, split_enc = h->mode & SYL_SPLIT_ENC;
+  const bool split_proj = h->mode & SYL_SPLIT_FPROJ, split_pos = h->mode & SYL_SPLIT_POS, split_enc = h->mode & SYL_SPLIT_ENC;
 
   // conv1..conv6: A = overlapping-row view of the previous channels-last activation
   for (int i = 1; i <= 6; ++i) {
@@ -608,10 +616,11 @@ int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
                      (uint64_t)s * kC, (uint64_t)Lin * kC))
       return SYL_E_CUDA;
     op.p.N = kC;
-    op.p.n_pass = (i == 1 ? split_conv1 : split_conv) ? 3 : 1;
+    op.p.n_pass = conv_split(h->mode, i) ? 3 : 1;
     op.p.act = 1;
+    // the lo half of this layer's output is only needed if the NEXT conv runs split
     const bool ok = (i < 6) ? make_o_maps(h, op, nullptr, at<__half>(ws, L.act_hi[i]),
-                                          split_conv ? at<__half>(ws, L.act_lo[i]) : nullptr, kC)
+                                          conv_split(h->mode, i + 1) ? at<__half>(ws, L.act_lo[i]) : nullptr, kC)
                             : make_o_maps(h, op, at<float>(ws, L.conv6), nullptr, nullptr, kC);
     if (!ok) return SYL_E_CUDA;
   }
@@ -627,7 +636,7 @@ int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
     op.p.n_pass = split_proj ? 3 : 1;
     op.p.bias = h->proj.bias;
     op.p.valid_rows = at<int32_t>(ws, L.valid);
-    if (!make_o_maps(h, op, at<float>(ws, L.h), at<__half>(ws, L.h16_hi), split_proj ? at<__half>(ws, L.h16_lo) : nullptr, kH))
+    if (!make_o_maps(h, op, at<float>(ws, L.h), at<__half>(ws, L.h16_hi), split_pos ? at<__half>(ws, L.h16_lo) : nullptr, kH))
       return SYL_E_CUDA;
   }
   // positional conv (posconv.cuh): activation window resident in smem, weights stream per tap
@@ -640,7 +649,7 @@ int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
     if (!make_tmap(&op.o_map, at<float>(ws, L.pos), 4, 3, dims, str, 16, 32, 64, &h->err)) return SYL_E_CUDA;
     op.p.T = T;
     op.p.batches = batch;
-    op.p.n_pass = split_proj ? 3 : 1;
+    op.p.n_pass = split_pos ? 3 : 1;
     op.p.bias = h->pos.bias;
     op.p.use_base_offset = posconv_base_offset_mode();
   }
@@ -716,22 +725,43 @@ void launch_ln(const float* x, const float* add, const float* g, const float* b,
   layernorm_rows_kernel<D><<<(rows + warps - 1) / warps, warps * 32, 0, st>>>(x, add, g, b, rows, of, ohi, olo);
 }
 
+long long* g_attn_trace = nullptr;   // set by syl_attention_trace for one launch
+int g_attn_trace_cap = 0;
+
 int launch_attention(const CUtensorMap& qkv, const CUtensorMap& o_hi, const CUtensorMap& o_lo, const int32_t* kv_len,
                      int B, int T, int out_lo, int sm_count, cudaStream_t st) {
   AttnParams ap;
+  ap.trace = g_attn_trace;
+  ap.trace_cap = g_attn_trace_cap;
   ap.T = T;
   ap.batches = B;
   ap.heads = kHeads;
   ap.model_dim = kH;
   ap.kv_len = kv_len;
   ap.out_lo = out_lo;
-  {
+  // experiment switches (profiles/r02_attention.md): SYL_ATTN_IMPL=6 selects the lock-step kernel, SYL_ATTN_POLY the
+  // number of exp2 pairs (out of every four) computed on the FMA pipe, SYL_ATTN_DEBUG the arithmetic-removal probes
+  static int impl = -1, debug = 0, poly = 0;
+  if (impl < 0) {
     const char* e = getenv("SYL_ATTN_DEBUG");
-    ap.debug = e ? atoi(e) : 0;
+    debug = e ? atoi(e) : 0;
+    e = getenv("SYL_ATTN_POLY");
+    poly = e ? atoi(e) : 1;
+    e = getenv("SYL_ATTN_IMPL");
+    impl = e ? atoi(e) : 7;
   }
+  ap.debug = debug;
   const int q_tiles = (T + ATT_BQ - 1) / ATT_BQ;
   const int items = B * kHeads * ((q_tiles + ATT_QT - 1) / ATT_QT);
-  attention_kernel<<<std::min(items, sm_count), ATT_THREADS, ATT_SMEM_TOTAL, st>>>(qkv, o_hi, o_lo, ap);
+  const int grid = std::min(items, sm_count);
+  if (impl == 6)
+    attention_kernel<<<grid, ATT_THREADS, ATT_SMEM_TOTAL, st>>>(qkv, o_hi, o_lo, ap);
+  else if (ap.trace)
+    attention7_kernel<0, true><<<grid, ATT7_THREADS, ATT7_SMEM_TOTAL, st>>>(qkv, o_hi, o_lo, ap);
+  else if (poly == 1)
+    attention7_kernel<1, false><<<grid, ATT7_THREADS, ATT7_SMEM_TOTAL, st>>>(qkv, o_hi, o_lo, ap);
+  else
+    attention7_kernel<0, false><<<grid, ATT7_THREADS, ATT7_SMEM_TOTAL, st>>>(qkv, o_hi, o_lo, ap);
   return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
 }
 
@@ -746,9 +776,22 @@ int run_frontend(syl_handle* h, const float* wav, cudaStream_t st) {
     conv0_moments_kernel<<<dim3(chunks, B), MOM_THREADS, 0, st>>>(wav, pl.t_samp, L0, at<double>(ws, L.mom));
     conv0_gn_coeff_kernel<<<B, kC, 0, st>>>(at<double>(ws, L.mom), chunks, h->conv0_w, h->gn_g, h->gn_b, L0,
                                             at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift));
-    conv0_apply_kernel<<<dim3((L0 + C0A_T - 1) / C0A_T, B), C0A_THREADS, 0, st>>>(
-        wav, pl.t_samp, L0, h->conv0_w, at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift),
-        at<__half>(ws, L.act_hi[0]), (h->mode & SYL_SPLIT_CONV1) ? at<__half>(ws, L.act_lo[0]) : nullptr);
+    __half* hi = at<__half>(ws, L.act_hi[0]);
+    __half* lo = conv_split(h->mode, 1) ? at<__half>(ws, L.act_lo[0]) : nullptr;
+    static int conv0_impl = -1;        // SYL_CONV0_IMPL=0: the FFMA kernel (kept for A/B timing), default: mma.sync
+    if (conv0_impl < 0) {
+      const char* e = getenv("SYL_CONV0_IMPL");
+      conv0_impl = e ? atoi(e) : 1;
+    }
+    if (conv0_impl == 0)
+      conv0_apply_kernel<<<dim3((L0 + C0A_T - 1) / C0A_T, B), C0A_THREADS, 0, st>>>(
+          wav, pl.t_samp, L0, h->conv0_w, at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift), hi, lo);
+    else if (lo)
+      conv0_mma_kernel<true><<<dim3((L0 + C0M_T - 1) / C0M_T, B), C0M_THREADS, 0, st>>>(
+          wav, pl.t_samp, L0, h->conv0_w, at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift), hi, lo);
+    else
+      conv0_mma_kernel<false><<<dim3((L0 + C0M_T - 1) / C0M_T, B), C0M_THREADS, 0, st>>>(
+          wav, pl.t_samp, L0, h->conv0_w, at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift), hi, lo);
   }
   CUDA_TRY(h, cudaGetLastError());
   {
@@ -855,6 +898,8 @@ int syl_create(syl_handle** out, int device, int n_layers, int mode) {
   syl_handle* h = new syl_handle();
   h->device = device;
   h->n_layers = n_layers;
+  if (mode & SYL_SPLIT_CONV) mode |= SYL_SPLIT_CONV2 | SYL_SPLIT_CONV3 | SYL_SPLIT_CONV4 | SYL_SPLIT_CONV5 | SYL_SPLIT_CONV6;
+  if (mode & SYL_SPLIT_PROJ) mode |= SYL_SPLIT_FPROJ | SYL_SPLIT_POS;
   h->mode = mode;
   h->sm_count = prop.multiProcessorCount;
   *out = h;
@@ -992,7 +1037,7 @@ static int enqueue_forward(syl_handle* h, Plan& pl, const float* wav, const int3
   void* workspace = pl.ws;
   const int batch = pl.batch;
   const int T = L.T, M = batch * T;
-  const bool split_proj = h->mode & SYL_SPLIT_PROJ, split_enc = h->mode & SYL_SPLIT_ENC;
+  const bool split_proj = h->mode & SYL_SPLIT_FPROJ, split_enc = h->mode & SYL_SPLIT_ENC;
   int rc;
   if (n_samples)
     valid_frames_kernel<<<(batch + 127) / 128, 128, 0, st>>>(n_samples, batch, T, at<int32_t>(workspace, L.valid));
@@ -1149,7 +1194,10 @@ int syl_encoder_layer(syl_handle* h, int layer, const float* h_in, const int32_t
 int syl_attention(const void* qkv_f16, const int32_t* kv_len, int batch, int T, void* out_f16, void* stream) {
   std::string err;
   if (!qkv_f16 || !out_f16 || batch <= 0 || T <= 0) return fail(nullptr, SYL_E_ARG, "syl_attention: bad arguments");
-  if (cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL) != cudaSuccess)
+  if (cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL) != cudaSuccess ||
+      cudaFuncSetAttribute(attention7_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL) != cudaSuccess ||
+      cudaFuncSetAttribute(attention7_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL) != cudaSuccess ||
+      cudaFuncSetAttribute(attention7_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL) != cudaSuccess)
     return fail(nullptr, SYL_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
   CUtensorMap map, omap;
   uint64_t dims[3] = {(uint64_t)3 * kH, (uint64_t)T, (uint64_t)batch};
@@ -1164,6 +1212,17 @@ int syl_attention(const void* qkv_f16, const int32_t* kv_len, int batch, int T, 
   if (launch_attention(map, omap, omap, kv_len, batch, T, 0, sms, reinterpret_cast<cudaStream_t>(stream)) != SYL_OK)
     return fail(nullptr, SYL_E_CUDA, "attention launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   return SYL_OK;
+}
+
+int syl_attention_trace(const void* qkv_f16, const int32_t* kv_len, int batch, int T, void* out_f16, void* trace_dev,
+                        int trace_cap, void* stream) {
+  if (!trace_dev || trace_cap <= 0) return fail(nullptr, SYL_E_ARG, "syl_attention_trace: bad arguments");
+  g_attn_trace = reinterpret_cast<long long*>(trace_dev);
+  g_attn_trace_cap = trace_cap;
+  const int rc = syl_attention(qkv_f16, kv_len, batch, T, out_f16, stream);
+  g_attn_trace = nullptr;
+  g_attn_trace_cap = 0;
+  return rc;
 }
 
 size_t syl_segment_workspace_bytes(int batch, int T) {
@@ -1305,7 +1364,7 @@ int syl_read_stage(syl_handle* h, const char* name, float* out, size_t n_floats,
     const int i = s[4] - '0';
     const size_t n = B * L.L[i] * kC;
     if (n_floats < n) return fail(h, SYL_E_ARG, "syl_read_stage: output too small (%zu < %zu)", n_floats, n);
-    const bool has_lo = (i == 0) ? (h->mode & SYL_SPLIT_CONV1) : (h->mode & SYL_SPLIT_CONV);
+    const bool has_lo = conv_split(h->mode, i + 1);
     join_f16_kernel<<<grid_for(n), 256, 0, st>>>(at<__half>(pl.ws, L.act_hi[i]), has_lo ? at<__half>(pl.ws, L.act_lo[i]) : nullptr,
                                                  out, n);
     return SYL_OK;

@@ -167,6 +167,124 @@ conv0_apply_kernel(const float* __restrict__ wav, int t_samp, int L0, const floa
 }
 
 // ----------------------------------------------------------------------------------------------
+// conv0 + GroupNorm + GELU with the 10-tap dot products on the tensor cores (warp-level mma.sync m16n8k16).
+// conv0_apply_kernel above is bound by instruction issue: 10 FFMA + ~13 other instructions per output element.
+// Here a warp computes [16 frames] x [8 channels] x [K = 16: taps 0-9, zero padded] per MMA; the fp32 waveform and
+// weights enter as fp16 hi + lo and three MMAs (hi*hi, lo*hi, hi*lo) accumulate in fp32, which keeps 22 significant
+// bits of both operands (the GEMM kernels' split scheme).  What remains per element is the GroupNorm FFMA2, the GELU
+// and the fp16 conversion.  tcgen05 is not used here on purpose: K = 10 and one TMEM round trip per 512-channel row
+// would cost more than the MMA saves, while mma.sync keeps the accumulator in the registers the epilogue needs.
+//
+// grid (ceil(L0 / 256), B), block 128: warp w owns channels [128 w, 128 w + 128) of every frame of the block and
+// keeps the B fragments of its 16 channel octets in registers.  Inside a group of four octets the MMA columns are
+// permuted so that a lane ends up with 8 CONSECUTIVE channels per frame row, i.e. one 16-byte store:
+//     MMA column n of octet jj in group grp  <->  channel 128 w + 32 grp + 8 (n >> 1) + 2 jj + (n & 1)
+// ----------------------------------------------------------------------------------------------
+constexpr int C0M_THREADS = 128;
+constexpr int C0M_T = 256;       // frames per block = 16 frame tiles of 16
+
+__device__ __forceinline__ void mma_m16n8k16_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <bool kLo>
+__global__ void __launch_bounds__(C0M_THREADS, 4)
+conv0_mma_kernel(const float* __restrict__ wav, int t_samp, int L0, const float* __restrict__ w0,
+                 const float* __restrict__ scale, const float* __restrict__ shift, __half* __restrict__ out_hi,
+                 __half* __restrict__ out_lo) {
+  __shared__ float xs[C0M_T * C0_S + 16];
+  __shared__ __align__(16) float s_sc[C0_OUT];
+  __shared__ __align__(16) float s_sh[C0_OUT];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * C0M_T;
+  const int nt = min(C0M_T, L0 - t0);
+  const float* w = wav + (size_t)b * t_samp + (size_t)t0 * C0_S;
+  const int nsamp = nt * C0_S + (C0_K - C0_S);
+  for (int i = threadIdx.x; i < C0M_T * C0_S + 16; i += C0M_THREADS) xs[i] = (i < nsamp) ? w[i] : 0.0f;
+  for (int i = threadIdx.x; i < C0_OUT; i += C0M_THREADS) {
+    s_sc[i] = scale[b * C0_OUT + i];
+    s_sh[i] = shift[b * C0_OUT + i];
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tig = lane & 3;
+  // B fragments (weights, "col" operand): this lane holds column n = g of every octet, k = 2 tig, 2 tig + 1 (b0) and
+  // k = 2 tig + 8, 2 tig + 9 (b1); taps >= 10 are zero
+  uint32_t bh[16][2], bl[16][2];
+#pragma unroll
+  for (int o = 0; o < 16; ++o) {
+    const int ch = warp * 128 + (o >> 2) * 32 + (g >> 1) * 8 + (o & 3) * 2 + (g & 1);
+    const float* wc = w0 + ch * C0_K;
+    const float w00 = wc[2 * tig], w01 = wc[2 * tig + 1];
+    const float w10 = (tig == 0) ? wc[8] : 0.0f, w11 = (tig == 0) ? wc[9] : 0.0f;
+    split_pair(w00, w01, bh[o][0], bl[o][0]);
+    split_pair(w10, w11, bh[o][1], bl[o][1]);
+  }
+  __syncthreads();
+
+  const int ch0 = warp * 128 + tig * 8;         // + 32 grp: the 8 consecutive channels of this lane in group grp
+  for (int ft = 0; ft < C0M_T / 16; ++ft) {
+    if (ft * 16 >= nt) break;
+    // A fragments (waveform windows, row-major 16 x 16): rows g and g + 8, k as for B
+    uint32_t ah[4], al[4];
+    {
+      const float* x0 = xs + (ft * 16 + g) * C0_S;
+      const float* x1 = x0 + 8 * C0_S;
+      split_pair(x0[2 * tig], x0[2 * tig + 1], ah[0], al[0]);
+      split_pair(x1[2 * tig], x1[2 * tig + 1], ah[1], al[1]);
+      const float e00 = (tig == 0) ? x0[8] : 0.0f, e01 = (tig == 0) ? x0[9] : 0.0f;
+      const float e10 = (tig == 0) ? x1[8] : 0.0f, e11 = (tig == 0) ? x1[9] : 0.0f;
+      split_pair(e00, e01, ah[2], al[2]);
+      split_pair(e10, e11, ah[3], al[3]);
+    }
+    const int r0 = ft * 16 + g, r1 = r0 + 8;
+    const size_t o0 = ((size_t)b * L0 + t0 + r0) * C0_OUT + ch0;
+    const size_t o1 = o0 + (size_t)8 * C0_OUT;
+#pragma unroll
+    for (int grp = 0; grp < 4; ++grp) {
+      const float4 sc0 = *reinterpret_cast<const float4*>(s_sc + ch0 + grp * 32);
+      const float4 sc1 = *reinterpret_cast<const float4*>(s_sc + ch0 + grp * 32 + 4);
+      const float4 sh0 = *reinterpret_cast<const float4*>(s_sh + ch0 + grp * 32);
+      const float4 sh1 = *reinterpret_cast<const float4*>(s_sh + ch0 + grp * 32 + 4);
+      const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+      const float shv[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+      uint32_t h0[4], h1[4], l0[4], l1[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int o = grp * 4 + jj;
+        float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        mma_m16n8k16_f16(c, al, bh[o][0], bh[o][1]);     // small terms first
+        mma_m16n8k16_f16(c, ah, bl[o][0], bl[o][1]);
+        mma_m16n8k16_f16(c, ah, bh[o][0], bh[o][1]);
+        // c[0], c[1]: row g, channels ch0 + 32 grp + 2 jj + {0, 1};  c[2], c[3]: row g + 8, same channels
+        const f32x2 sc2 = pack2(scv[2 * jj], scv[2 * jj + 1]), sh2 = pack2(shv[2 * jj], shv[2 * jj + 1]);
+        float y0, y1, y2, y3;
+        unpack2(fma2(pack2(c[0], c[1]), sc2, sh2), y0, y1);
+        unpack2(fma2(pack2(c[2], c[3]), sc2, sh2), y2, y3);
+        gelu_fast2(y0, y1, y0, y1);
+        gelu_fast2(y2, y3, y2, y3);
+        if (kLo) {
+          split_pair(y0, y1, h0[jj], l0[jj]);
+          split_pair(y2, y3, h1[jj], l1[jj]);
+        } else {
+          h0[jj] = pack_f16x2_sat(y0, y1);
+          h1[jj] = pack_f16x2_sat(y2, y3);
+        }
+      }
+      if (r0 < nt) {
+        *reinterpret_cast<uint4*>(out_hi + o0 + grp * 32) = make_uint4(h0[0], h0[1], h0[2], h0[3]);
+        if (kLo) *reinterpret_cast<uint4*>(out_lo + o0 + grp * 32) = make_uint4(l0[0], l0[1], l0[2], l0[3]);
+      }
+      if (r1 < nt) {
+        *reinterpret_cast<uint4*>(out_hi + o1 + grp * 32) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
+        if (kLo) *reinterpret_cast<uint4*>(out_lo + o1 + grp * 32) = make_uint4(l1[0], l1[1], l1[2], l1[3]);
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // Row LayerNorm (eps 1e-5), one warp per row, D in {512, 768}:
 //    y = LN(x (+ add)) * gamma + beta  ->  fp32 and / or fp16 hi (+ lo)
 // ----------------------------------------------------------------------------------------------

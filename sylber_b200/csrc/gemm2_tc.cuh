@@ -18,14 +18,18 @@
 
 namespace syl {
 
-constexpr int GEMM2_STAGES = 6;
 constexpr int GEMM2_A_BYTES = 128 * GEMM_BLOCK_K * 2;   // 16 KB: this CTA's 128 rows of the 256-row M tile
 constexpr int GEMM2_B_BYTES = 128 * GEMM_BLOCK_K * 2;   // 16 KB: this CTA's 128 of the 256 N rows
 constexpr int GEMM2_STAGE_BYTES = GEMM2_A_BYTES + GEMM2_B_BYTES;
+
+// A double-buffered epilogue staging (two 4 KB buffers per warp, 5 smem stages, wait_group.read 1) was measured in
+// round 2 and brought nothing (QKV 0.507 vs 0.474 ms): the epilogue is not waiting for its bulk stores.
+constexpr int GEMM2_STAGES = 6;
 constexpr int GEMM2_SMEM_EPI = GEMM2_STAGES * GEMM2_STAGE_BYTES;
 constexpr int GEMM2_SMEM_BIAS = GEMM2_SMEM_EPI + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES;
 constexpr int GEMM2_SMEM_BAR = GEMM2_SMEM_BIAS + 2 * GEMM_BLOCK_N * 4;
 constexpr int GEMM2_SMEM_TOTAL = GEMM2_SMEM_BAR + 256;
+static_assert(GEMM2_SMEM_TOTAL <= 232448, "shared memory budget");
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -217,16 +221,18 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
     const int half = ew >> 2;                // which 128-column half of the tile
     const int lane = (int)lane_id();
     const int epi_tid = threadIdx.x - GEMM_EPI_WARP0 * 32;   // 0..255
-    uint8_t* stage_buf = smem_epi + ew * GEMM_EPI_STAGE_BYTES;
-    // swizzled staging addresses of this lane's row: 128-byte rows (fp32) and 64-byte rows (fp16)
-    uint8_t* row128 = stage_buf + lane * 128;
-    uint8_t* row64_hi = stage_buf + lane * 64;
-    uint8_t* row64_lo = stage_buf + 2048 + lane * 64;
+    uint8_t* stage_base = smem_epi + ew * GEMM_EPI_STAGE_BYTES;
     const int sw128 = lane & 7;
     const int sw64 = (lane >> 1) & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
     int it = 0;
+    // staging buffer for the next bulk store, free to be overwritten when this returns
+    auto acquire = [&]() -> uint8_t* {
+      if (lane == 0) tma_store_wait_read();   // the previous bulk store has finished reading it
+      __syncwarp();
+      return stage_base;
+    };
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int n_tile = tile % tiles_n;
       const int m_tile = tile / tiles_n;
@@ -236,10 +242,12 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
       const bool warp_ok = warp_row0 < p.rows_per_batch;
       const bool zero_row = p.valid_rows != nullptr && row_in_batch >= __ldg(p.valid_rows + batch);
       const float scale = (n_tile * GEMM_BLOCK_N < p.col_scale_limit) ? p.col_scale : 1.0f;
-      // stage this tile's bias in shared memory (one column per epilogue thread, double buffered by tile parity)
+      // stage this tile's bias (pre-multiplied by the column scale, a power of two) in shared memory: one column per
+      // epilogue thread, double buffered by tile parity
       float* sbias = smem_bias + (it & 1) * GEMM_BLOCK_N;
-      sbias[epi_tid] = p.bias ? __ldg(p.bias + n_tile * GEMM_BLOCK_N + epi_tid) : 0.0f;
+      sbias[epi_tid] = p.bias ? __ldg(p.bias + n_tile * GEMM_BLOCK_N + epi_tid) * scale : 0.0f;
       named_bar_sync(1, GEMM_EPI_WARPS * 32);
+      const f32x2 scale2 = pack2(scale, scale);
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
@@ -256,10 +264,11 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4 bb = b4[i];
-          v[4 * i + 0] = (__uint_as_float(r[c & 1][4 * i + 0]) + bb.x) * scale;
-          v[4 * i + 1] = (__uint_as_float(r[c & 1][4 * i + 1]) + bb.y) * scale;
-          v[4 * i + 2] = (__uint_as_float(r[c & 1][4 * i + 2]) + bb.z) * scale;
-          v[4 * i + 3] = (__uint_as_float(r[c & 1][4 * i + 3]) + bb.w) * scale;
+          // (acc + bias) * scale == acc * scale + bias * scale exactly: scale is a power of two
+          unpack2(fma2(pack2(__uint_as_float(r[c & 1][4 * i + 0]), __uint_as_float(r[c & 1][4 * i + 1])), scale2, pack2(bb.x, bb.y)),
+                  v[4 * i + 0], v[4 * i + 1]);
+          unpack2(fma2(pack2(__uint_as_float(r[c & 1][4 * i + 2]), __uint_as_float(r[c & 1][4 * i + 3])), scale2, pack2(bb.z, bb.w)),
+                  v[4 * i + 2], v[4 * i + 3]);
         }
         if (p.act == 1) {
 #pragma unroll
@@ -271,28 +280,34 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
         }
         if (warp_ok) {
           if (p.out_f32) {
-            if (lane == 0) tma_store_wait_read();   // previous bulk store has finished reading the staging buffer
-            __syncwarp();
+            uint8_t* buf = acquire();
+            uint8_t* row128 = buf + lane * 128;
 #pragma unroll
             for (int i = 0; i < 8; ++i)
               *reinterpret_cast<float4*>(row128 + ((i ^ sw128) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_3d(&o_f32, stage_buf, col0, warp_row0, batch);
+              tma_store_3d(&o_f32, buf, col0, warp_row0, batch);
               tma_store_commit();
             }
           }
           if (p.out_hi) {
             uint32_t hi[16], lo[16];
+            if (p.out_lo) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) split_pair(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
-            if (lane == 0) tma_store_wait_read();
-            __syncwarp();
+              for (int i = 0; i < 16; ++i) split_pair(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) hi[i] = pack_f16x2_sat(v[2 * i], v[2 * i + 1]);
+            }
+            uint8_t* buf = acquire();
+            uint8_t* row64_hi = buf + lane * 64;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               *reinterpret_cast<uint4*>(row64_hi + ((i ^ sw64) << 4)) = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
             if (p.out_lo) {
+              uint8_t* row64_lo = buf + 2048 + lane * 64;
 #pragma unroll
               for (int i = 0; i < 4; ++i)
                 *reinterpret_cast<uint4*>(row64_lo + ((i ^ sw64) << 4)) = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
@@ -300,8 +315,8 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_3d(&o_hi, stage_buf, col0, warp_row0, batch);
-              if (p.out_lo) tma_store_3d(&o_lo, stage_buf + 2048, col0, warp_row0, batch);
+              tma_store_3d(&o_hi, buf, col0, warp_row0, batch);
+              if (p.out_lo) tma_store_3d(&o_lo, buf + 2048, col0, warp_row0, batch);
               tma_store_commit();
             }
           }

@@ -117,11 +117,53 @@ class _Engine:
         return ws, need
 
     def side_streams(self, n):
+        """Sub-batch streams in descending priority: the first sub-batch's kernels win every scheduling decision, so
+        it finishes (and its device->host copy starts) while the second one computes, instead of both interleaving
+        kernel by kernel and exposing both result copies at the end.  CUDA-graph nodes capture the priority of the
+        stream they were captured on."""
+        lo, hi = torch.cuda.Stream.priority_range()      # (least, greatest) = (0, -5) on current parts
         while len(self._streams) < n:
-            self._streams.append(torch.cuda.Stream(device=self.device))
+            prio = max(hi, min(lo, hi + len(self._streams)))
+            self._streams.append(torch.cuda.Stream(device=self.device, priority=prio))
         return self._streams[:n]
 
-    def stage_input(self, rows, max_length, slot=0):
+    @staticmethod
+    def _as_block(rows, max_length):
+        """(B, max_length) view if the rows are consecutive full-length slices of one contiguous tensor, else None."""
+        r0 = rows[0]
+        if r0.dtype != torch.float32 or r0.device.type != "cpu" or not r0.is_contiguous() or r0.shape[-1] != max_length:
+            return None
+        p0, step = r0.data_ptr(), max_length * 4
+        for i, r in enumerate(rows):
+            if (r.dtype != torch.float32 or r.shape[-1] != max_length or not r.is_contiguous() or
+                    r.data_ptr() != p0 + i * step or r.untyped_storage().data_ptr() != r0.untyped_storage().data_ptr()):
+                return None
+        return torch.as_strided(r0, (len(rows), max_length), (max_length, 1))
+
+    def upload(self, rows, lengths, max_length, slot):
+        """Host rows -> the slot's persistent (B, max_length) device batch, on the current stream.
+
+        Rows that already sit in pinned memory are copied straight from where they are (one 2-D copy when they are
+        consecutive slices of one tensor, else one copy per row); pageable rows go through the slot's pinned staging
+        buffer.  Short rows are zero padded (sylber.py:107-111)."""
+        B = len(rows)
+        wav_dev, n_dev = self.device_input(slot, B, max_length)
+        block = self._as_block(rows, max_length)
+        if block is not None and block.is_pinned():
+            wav_dev.copy_(block, non_blocking=True)
+        elif all(r.device.type == "cpu" and r.dtype == torch.float32 and r.is_pinned() for r in rows):
+            for i, r in enumerate(rows):
+                k = r.shape[-1]
+                wav_dev[i, :k].copy_(r.reshape(-1), non_blocking=True)
+                if k < max_length:
+                    wav_dev[i, k:].zero_()
+        else:
+            wav_dev.copy_(self.stage_input(rows, max_length, slot, block), non_blocking=True)
+        n_host = torch.tensor(lengths, dtype=torch.int32)
+        n_dev.copy_(n_host, non_blocking=True)
+        return wav_dev, n_dev
+
+    def stage_input(self, rows, max_length, slot=0, block=None):
         """Zero-padded (B, max_length) fp32 batch in a persistent pinned buffer (consumed within the call)."""
         B = len(rows)
         n = B * max_length
@@ -129,6 +171,9 @@ class _Engine:
         if buf is None or buf.numel() < n:
             buf = self._stage_in[slot] = torch.empty(n, dtype=torch.float32, pin_memory=True)
         host = buf[:n].view(B, max_length)
+        if block is not None:
+            host.copy_(block)
+            return host
         for i, r in enumerate(rows):
             k = r.shape[-1]
             host[i, :k].copy_(r)
@@ -270,7 +315,7 @@ class Segmenter:
       * missing checkpoint tensors raise (the reference's strict=False at :52 ignores them).
       * extra keyword arguments: `state_dict=` (use these tensors instead of loading `model_ckpt`),
         `mode=` ("parity" default | "strict" | "fast" | "exact", see include/sylber_b200.h), `max_batch=`,
-        `streams=` (sub-batches in flight, default 2: copies of one overlap kernels of the other).
+        `streams=` (sub-batches in flight, default 3: copies of one overlap kernels of the others).
     """
 
     def __init__(self,
@@ -285,7 +330,7 @@ class Segmenter:
         state_dict = kwargs.pop("state_dict", None)
         mode = kwargs.pop("mode", "parity")
         self.max_batch = int(kwargs.pop("max_batch", 64))
-        self.streams = int(kwargs.pop("streams", 2))
+        self.streams = int(kwargs.pop("streams", 3))
         self.enc_dim = HIDDEN
         self.encoding_layer = encoding_layer
         self.ema_decay = ema_decay
@@ -366,13 +411,9 @@ class Segmenter:
             chunk = rows[lo:hi]
             if k >= len(streams):                      # this slot's staging buffer and workspace are about to be reused
                 st.synchronize()
-            host = eng.stage_input(chunk, max_length, slot)
-            n_host = torch.tensor(lengths[lo:hi], dtype=torch.int32)
             st.wait_stream(main)
             with torch.cuda.stream(st):
-                wav_dev, n_dev = eng.device_input(slot, hi - lo, max_length)
-                wav_dev.copy_(host, non_blocking=True)
-                n_dev.copy_(n_host, non_blocking=True)
+                wav_dev, n_dev = eng.upload(chunk, lengths[lo:hi], max_length, slot)
                 hidden, seg, cnt, feat = eng.forward(wav_dev, n_dev, thr_n, thr_m, slot=slot)
                 hidden_h, hidden_pin = eng.pool.array(tuple(hidden.shape))
                 hidden_pin.copy_(hidden, non_blocking=True)
