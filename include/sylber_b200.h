@@ -100,6 +100,19 @@ int syl_attention(const void* qkv_f16, const int32_t* kv_len, int batch, int T, 
  * trace_dev[7][trace_cap] (int64 device memory, zero it first); decoded by tools/attn_trace.py */
 int syl_attention_trace(const void* qkv_f16, const int32_t* kv_len, int batch, int T, void* out_f16, void* trace_dev,
                         int trace_cap, void* stream);
+/* ---- the steps either side of the path ----
+ * Front door, replaces the host preprocessing of sylber/model/sylber.py:83-87 (file branch) and :93-118 (padding):
+ * pcm holds the utterances' 16 kHz int16 samples back to back on the device, utterance b = pcm[offsets[b] ..
+ * offsets[b] + n_samples[b]); wav_out[b, :] = (x / 32768 - mean) / std (unbiased std, like torch.std) when
+ * normalize != 0, else x / 32768; zero padded to t_samp_max.  workspace >= syl_pcm16_workspace_bytes. */
+size_t syl_pcm16_workspace_bytes(int batch, int t_samp_max);
+int syl_prepare_pcm16(const int16_t* pcm, const int64_t* offsets, const int32_t* n_samples, int batch, int t_samp_max,
+                      int normalize, float* wav_out, void* workspace, size_t workspace_bytes, void* stream);
+/* Back door, replaces the codebook search of KMQuantizer.get_indices (sylber/model/quantizer.py:86-110):
+ * idx_out[r] = argmin_k |x_r - c_k|^2 over centroids [K, 768] (first minimum wins); normalize != 0 applies
+ * x / sqrt(sum x^2 + 1e-8) * 6 first (quantizer.py:99); dist_out (optional) receives the squared distances. */
+int syl_kmeans_assign(const float* feats, int n, const float* centroids, int K, int normalize, int32_t* idx_out,
+                      float* dist_out, void* stream);
 /* segmentation + pooling on given states [batch, T, 768] fp32; workspace >= syl_segment_workspace_bytes */
 size_t syl_segment_workspace_bytes(int batch, int T);
 int syl_segment(const float* states, int batch, int T, float thr_norm, float thr_merge, int32_t* seg,

@@ -6,8 +6,11 @@ output contract.  All arithmetic runs in hand-written CUDA kernels behind the C 
 include/sylber_b200.h (libsylber_b200.so); PyTorch is used for device memory, streams and
 torch.distributed only.  There is no CPU fallback.
 """
-from .segmenter import Segmenter, SpeechModel  # noqa: F401
+from .segmenter import Segmenter, SpeechModel, KMeansQuantizer  # noqa: F401
+from .thresholder import Thresholder  # noqa: F401
+from .batching import plan_length_buckets  # noqa: F401
 from ._lib import build_library, load_library, library_path  # noqa: F401
 
-__all__ = ["Segmenter", "SpeechModel", "build_library", "load_library", "library_path"]
+__all__ = ["Segmenter", "SpeechModel", "KMeansQuantizer", "Thresholder", "plan_length_buckets", "build_library",
+           "load_library", "library_path"]
 __version__ = "0.1.0"

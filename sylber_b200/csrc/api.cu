@@ -16,6 +16,7 @@
 #include "../../include/sylber_b200.h"
 #include "attention.cuh"
 #include "frontend.cuh"
+#include "frontdoor.cuh"
 #include "gemm_tc.cuh"
 #include "gemm2_tc.cuh"
 #include "posconv.cuh"
@@ -1223,6 +1224,34 @@ int syl_attention_trace(const void* qkv_f16, const int32_t* kv_len, int batch, i
   g_attn_trace = nullptr;
   g_attn_trace_cap = 0;
   return rc;
+}
+
+size_t syl_pcm16_workspace_bytes(int batch, int t_samp_max) {
+  if (batch <= 0 || t_samp_max <= 0) return 0;
+  return (size_t)batch * ((t_samp_max + PCM_CHUNK - 1) / PCM_CHUNK) * 2 * sizeof(double);
+}
+
+int syl_prepare_pcm16(const int16_t* pcm, const int64_t* offsets, const int32_t* n_samples, int batch, int t_samp_max,
+                      int normalize, float* wav_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!pcm || !offsets || !n_samples || !wav_out || !workspace || batch <= 0 || t_samp_max <= 0)
+    return fail(nullptr, SYL_E_ARG, "syl_prepare_pcm16: bad arguments");
+  if (workspace_bytes < syl_pcm16_workspace_bytes(batch, t_samp_max))
+    return fail(nullptr, SYL_E_WORKSPACE, "syl_prepare_pcm16: workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int chunks = (t_samp_max + PCM_CHUNK - 1) / PCM_CHUNK;
+  double* part = reinterpret_cast<double*>(workspace);
+  if (normalize) pcm16_stats_kernel<<<dim3(chunks, batch), PCM_THREADS, 0, st>>>(pcm, offsets, n_samples, chunks, part);
+  pcm16_apply_kernel<<<dim3(chunks, batch), PCM_THREADS, 0, st>>>(pcm, offsets, n_samples, chunks, part, normalize, t_samp_max, wav_out);
+  return cudaGetLastError() == cudaSuccess ? SYL_OK : fail(nullptr, SYL_E_CUDA, "syl_prepare_pcm16 launch failed");
+}
+
+int syl_kmeans_assign(const float* feats, int n, const float* centroids, int K, int normalize, int32_t* idx_out,
+                      float* dist_out, void* stream) {
+  if (n == 0) return SYL_OK;
+  if (!feats || !centroids || !idx_out || n < 0 || K <= 0) return fail(nullptr, SYL_E_ARG, "syl_kmeans_assign: bad arguments");
+  kmeans_assign_kernel<<<(n + KM_ROWS - 1) / KM_ROWS, KM_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      feats, n, centroids, K, normalize, idx_out, dist_out);
+  return cudaGetLastError() == cudaSuccess ? SYL_OK : fail(nullptr, SYL_E_CUDA, "syl_kmeans_assign launch failed");
 }
 
 size_t syl_segment_workspace_bytes(int batch, int T) {

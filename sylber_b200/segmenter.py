@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .batching import plan_length_buckets
 from .weights import normalize_state_dict, random_hubert_state_dict, REQUIRED_KEYS
 
 HIDDEN = 768
@@ -162,6 +163,52 @@ class _Engine:
         n_host = torch.tensor(lengths, dtype=torch.int32)
         n_dev.copy_(n_host, non_blocking=True)
         return wav_dev, n_dev
+
+    def upload_pcm16(self, rows, lengths, max_length, slot):
+        """int16 PCM rows -> the slot's (B, max_length) fp32 device batch, converted, z-normalised and zero padded on
+        the GPU (syl_prepare_pcm16, sylber.py:83-87 + :93-118).  The samples travel back to back as int16."""
+        B = len(rows)
+        total = sum(lengths)
+        key = ("pcm", slot)
+        buf = self._stage_in.get(key)
+        if buf is None or buf[0].numel() < total or buf[2].numel() < B:
+            cap = max(total, 1)
+            buf = self._stage_in[key] = (torch.empty(cap, dtype=torch.int16, pin_memory=True),
+                                         torch.empty(cap, dtype=torch.int16, device=self.device),
+                                         torch.empty(max(B, 64), dtype=torch.int64, device=self.device))
+        host, dev, off_dev = buf
+        offsets, o = [], 0
+        for r, n in zip(rows, lengths):
+            host[o:o + n].copy_(r)
+            offsets.append(o)
+            o += n
+        dev[:total].copy_(host[:total], non_blocking=True)
+        off_dev[:B].copy_(torch.tensor(offsets, dtype=torch.int64), non_blocking=True)
+        wav_dev, n_dev = self.device_input(slot, B, max_length)
+        n_dev.copy_(torch.tensor(lengths, dtype=torch.int32), non_blocking=True)
+        need = int(self.lib.syl_pcm16_workspace_bytes(B, max_length))
+        ws = self._stage_in.get(("pcm_ws", slot))
+        if ws is None or ws.numel() < need:
+            ws = self._stage_in[("pcm_ws", slot)] = torch.empty(need, dtype=torch.uint8, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self.lib.syl_prepare_pcm16(_ptr(dev), _ptr(off_dev), _ptr(n_dev), B, max_length, 1, _ptr(wav_dev), _ptr(ws), need,
+                                        ctypes.c_void_p(stream))
+        _lib.check(self.lib, None, rc, "syl_prepare_pcm16")
+        return wav_dev, n_dev
+
+    def segment_states(self, states, thr_norm, thr_merge):
+        """get_segment + pooling on given (B,T,768) fp32 device states (syl_segment)."""
+        B, T, _ = states.shape
+        need = int(self.lib.syl_segment_workspace_bytes(B, T))
+        ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        seg = torch.empty((B, T, 2), dtype=torch.int32, device=self.device)
+        cnt = torch.empty((B,), dtype=torch.int32, device=self.device)
+        feat = torch.empty((B, T, HIDDEN), dtype=torch.float32, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self.lib.syl_segment(_ptr(states), B, T, float(thr_norm), float(thr_merge), _ptr(seg), _ptr(cnt), _ptr(feat), T,
+                                  _ptr(ws), need, ctypes.c_void_p(stream))
+        _lib.check(self.lib, None, rc, "syl_segment")
+        return seg, cnt, feat
 
     def stage_input(self, rows, max_length, slot=0, block=None):
         """Zero-padded (B, max_length) fp32 batch in a persistent pinned buffer (consumed within the call)."""
@@ -315,6 +362,7 @@ class Segmenter:
       * missing checkpoint tensors raise (the reference's strict=False at :52 ignores them).
       * extra keyword arguments: `state_dict=` (use these tensors instead of loading `model_ckpt`),
         `mode=` ("parity" default | "strict" | "fast" | "exact", see include/sylber_b200.h), `max_batch=`,
+        `bucket_ratio=` (opt-in length-bucketed batching, batching.py), `thresholder=`,
         `streams=` (sub-batches in flight, default 3: copies of one overlap kernels of the others).
     """
 
@@ -331,6 +379,8 @@ class Segmenter:
         mode = kwargs.pop("mode", "parity")
         self.max_batch = int(kwargs.pop("max_batch", 64))
         self.streams = int(kwargs.pop("streams", 3))
+        self.bucket_ratio = kwargs.pop("bucket_ratio", None)       # e.g. 1.25: length-bucketed batching (batching.py)
+        self.thresholder = kwargs.pop("thresholder", None)         # sylber_b200.Thresholder for segment(normthreshold=None)
         self.enc_dim = HIDDEN
         self.encoding_layer = encoding_layer
         self.ema_decay = ema_decay
@@ -377,22 +427,13 @@ class Segmenter:
             batch_wavs = wav if is_batch else [wav]
         return batch_wavs, is_batch
 
-    @torch.no_grad()
-    def __call__(self, wav_file=None, wav=None, in_second=True):
-        """Same contract as the reference: a dict (single input) or list of dicts with
-        `segments` (N,2), `segment_features` (N,768) float32, `hidden_states` (T_max,768) float32."""
-        batch_wavs, is_batch = self._prepare(wav_file, wav)
+    # ------------------------------------------------------------------------------------------
+    def _run_rows(self, rows, lengths, max_length, pcm=False):
+        """One padded batch through the engine.  rows: 1-D fp32 CPU tensors (or int16 when `pcm`), every row padded to
+        `max_length`.  Returns per row (segments int64 (N,2) | empty, segment_features (N,768) | empty, hidden)."""
         eng = self._engine
-        rows = []
-        for w in batch_wavs:
-            w = torch.as_tensor(w)
-            if w.dim() == 1:
-                w = w[None, :]
-            rows.extend(w[i] for i in range(w.shape[0]))      # torch.cat(dim=0) at sylber.py:117: channels become rows
-        lengths = [int(r.shape[-1]) for r in rows]
-        max_length = max(lengths)
         # Sub-batches run on separate streams so that one sub-batch's host->device / device->host copies overlap the
-        # other's kernels.  Every sub-batch is padded to the batch-wide max_length: results depend on T_max (8a).
+        # others' kernels.  Every sub-batch is padded to the batch-wide max_length: results depend on T_max (8a).
         n_rows = len(rows)
         n_sub = max(1, min(self.streams, n_rows // 8)) if n_rows <= self.max_batch else 1
         bounds = []
@@ -413,14 +454,17 @@ class Segmenter:
                 st.synchronize()
             st.wait_stream(main)
             with torch.cuda.stream(st):
-                wav_dev, n_dev = eng.upload(chunk, lengths[lo:hi], max_length, slot)
+                if pcm:
+                    wav_dev, n_dev = eng.upload_pcm16(chunk, lengths[lo:hi], max_length, slot)
+                else:
+                    wav_dev, n_dev = eng.upload(chunk, lengths[lo:hi], max_length, slot)
                 hidden, seg, cnt, feat = eng.forward(wav_dev, n_dev, thr_n, thr_m, slot=slot)
                 hidden_h, hidden_pin = eng.pool.array(tuple(hidden.shape))
                 hidden_pin.copy_(hidden, non_blocking=True)
                 cnt_pin = torch.empty(cnt.shape, dtype=torch.int32, pin_memory=True)
                 cnt_pin.copy_(cnt, non_blocking=True)
             pending.append((st, lo, hi, hidden_h, hidden_pin, seg, cnt_pin, feat))
-        outputs = []
+        out = []
         for st, lo, hi, hidden_h, hidden_pin, seg, cnt_pin, feat in pending:
             st.synchronize()
             cnt_h = cnt_pin.numpy()
@@ -433,11 +477,124 @@ class Segmenter:
             del hidden_pin, feat_pin
             for i in range(hi - lo):
                 n = int(cnt_h[i])
-                segments = seg_h[i, :n].astype(np.int64) if n > 0 else np.array([])
-                outputs.append({
-                    'segments': segments * 1.0 / FRAME_RATE if in_second else segments,
-                    'segment_features': feat_h[i, :n] if n > 0 else np.array([]),
-                    'hidden_states': hidden_h[i],
-                })
+                out.append((seg_h[i, :n].astype(np.int64) if n > 0 else np.array([]),
+                            feat_h[i, :n] if n > 0 else np.array([]), hidden_h[i]))
         main.wait_stream(streams[0])
+        return out
+
+    @torch.no_grad()
+    def __call__(self, wav_file=None, wav=None, in_second=True, pcm16=None):
+        """Same contract as the reference: a dict (single input) or list of dicts with
+        `segments` (N,2), `segment_features` (N,768) float32, `hidden_states` (T_max,768) float32.
+
+        `pcm16=` (extension): one or a list of 1-D int16 arrays / tensors of 16 kHz mono PCM.  Equivalent to the
+        reference's file branch (x / 32768, then (w - mean) / std, sylber.py:83-87) with the conversion,
+        normalisation and padding done on the GPU (syl_prepare_pcm16) - half the host->device bytes."""
+        pcm = pcm16 is not None
+        if pcm:
+            is_batch = isinstance(pcm16, (list, tuple))
+            rows = [torch.as_tensor(np.ascontiguousarray(x) if isinstance(x, np.ndarray) else x).reshape(-1)
+                    for x in (pcm16 if is_batch else [pcm16])]
+            if any(r.dtype != torch.int16 for r in rows):
+                raise TypeError("pcm16 expects int16 samples")
+        else:
+            batch_wavs, is_batch = self._prepare(wav_file, wav)
+            rows = []
+            for w in batch_wavs:
+                w = torch.as_tensor(w)
+                if w.dim() == 1:
+                    w = w[None, :]
+                rows.extend(w[i] for i in range(w.shape[0]))      # torch.cat(dim=0) at sylber.py:117: channels become rows
+        lengths = [int(r.shape[-1]) for r in rows]
+        if self.bucket_ratio:
+            # opt-in deviation from the reference's padding semantics (batching.py): each bucket is padded to its own max
+            buckets = plan_length_buckets(lengths, self.bucket_ratio, self.max_batch)
+        else:
+            buckets = [list(range(len(rows)))]
+        results = [None] * len(rows)
+        for idx in buckets:
+            sub_len = [lengths[i] for i in idx]
+            for i, r in zip(idx, self._run_rows([rows[i] for i in idx], sub_len, max(sub_len), pcm)):
+                results[i] = r
+        outputs = [{'segments': seg * 1.0 / FRAME_RATE if in_second else seg,
+                    'segment_features': feat, 'hidden_states': hid} for seg, feat, hid in results]
         return outputs if is_batch else outputs[0]
+
+    @torch.no_grad()
+    def segment(self, input_values=None, features=None, attention_mask=None, mergethreshold=None, normthreshold=None,
+                **_kw):
+        """The torch-side contract of the reference's other inference caller, `Sylber.segment`
+        (sylber/model/sylber.py:208-247): returns `(features, segments, avg_fts)` with features (B,T,768) on the
+        device, segments a list of (N,2) int64 arrays (or the reference's empty float array) and avg_fts the per-segment
+        means zero-padded to (B, max(N,1), 768).  Segmentation and pooling run on the GPU (`syl_forward` /
+        `syl_segment`); thresholds default to the Segmenter's, or to `self.thresholder` when one is attached."""
+        eng = self._engine
+        if normthreshold is None:
+            thr = getattr(self, "thresholder", None)
+            normthreshold = float(thr.get_threshold()) if thr is not None else self.norm_threshold
+        if mergethreshold is None:
+            mergethreshold = self.merge_threshold
+        thr_n, thr_m = np.float32(normthreshold), np.float32(mergethreshold)
+        main = torch.cuda.current_stream(eng.device)
+        side = eng.side_streams(1)[0]
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            if features is None:
+                wav = input_values.to(device=eng.device, dtype=torch.float32).contiguous()
+                n = None
+                if attention_mask is not None:
+                    n = attention_mask.to(eng.device).sum(-1).to(torch.int32).contiguous()
+                hidden, seg, cnt, feat = eng.forward(wav, n, thr_n, thr_m, slot="segment")
+                features = hidden.clone()
+            else:
+                features = features.to(device=eng.device, dtype=torch.float32).contiguous()
+                seg, cnt, feat = eng.segment_states(features, thr_n, thr_m)
+            cnt_h = cnt.cpu().numpy()
+            n_max = max(int(cnt_h.max()) if len(cnt_h) else 0, 1)
+            seg_h = seg[:, :n_max].cpu().numpy()
+            avg = feat[:, :n_max].clone()
+            keep = torch.arange(n_max, device=eng.device)[None, :] < cnt[:, None].to(torch.int64)
+            avg = avg * keep[:, :, None]                       # pad_sequence(padding_value=0.0)
+        main.wait_stream(side)
+        segments = [seg_h[b, :int(cnt_h[b])].astype(np.int64) if cnt_h[b] > 0 else np.array([]) for b in range(len(cnt_h))]
+        return features, segments, avg
+
+
+class KMeansQuantizer:
+    """Nearest-centroid lookup of segment features: the inference half of the reference's `KMQuantizer`
+    (sylber/model/quantizer.py:86-135, `load_km_quantizer`), whose `vector_quantize_pytorch` codebook does an
+    exhaustive Euclidean search.  `centroids`: path to the reference's .npy file or an array (K, 768)."""
+
+    def __init__(self, centroids, normalize=False, device="cuda"):
+        if isinstance(centroids, (str, os.PathLike)):
+            centroids = np.load(centroids)
+        c = torch.as_tensor(np.asarray(centroids), dtype=torch.float32)
+        if c.dim() != 2 or c.shape[1] != HIDDEN:
+            raise ValueError(f"centroids must be (K, {HIDDEN}), got {tuple(c.shape)}")
+        if not torch.cuda.is_available():
+            raise RuntimeError("sylber_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load_library()
+        self.device = torch.device(device if "cuda" in str(device) else "cuda")
+        self.centroids = c.to(self.device).contiguous()
+        self.normalize = bool(normalize)
+
+    @torch.no_grad()
+    def get_indices(self, token, return_distance=False):
+        """token (..., 768) array or tensor -> int64 indices of shape token.shape[:-1] (quantizer.py:95-106)."""
+        t = torch.as_tensor(token)
+        lead = tuple(t.shape[:-1])
+        x = t.reshape(-1, HIDDEN).to(device=self.device, dtype=torch.float32).contiguous()
+        n = x.shape[0]
+        idx = torch.empty((n,), dtype=torch.int32, device=self.device)
+        dist = torch.empty((n,), dtype=torch.float32, device=self.device) if return_distance else None
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            rc = self.lib.syl_kmeans_assign(_ptr(x), n, _ptr(self.centroids), self.centroids.shape[0], int(self.normalize),
+                                            _ptr(idx), _ptr(dist), ctypes.c_void_p(stream))
+        _lib.check(self.lib, None, rc, "syl_kmeans_assign")
+        out = idx.to(torch.int64).reshape(lead)
+        return (out, dist.reshape(lead)) if return_distance else out
+
+    def decode(self, indices):
+        """quantizer.py:123-129: centroids of the given indices (negative indices clipped to 0)."""
+        return self.centroids[torch.as_tensor(indices, device=self.device).clip(0).long()]

@@ -1,0 +1,102 @@
+"""CPU: the host logic and oracles of the rows either side of the path: length bucketing, the
+Thresholder port against the reference class, the PCM normalisation oracle against the reference's own lines."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from sylber_b200.batching import plan_length_buckets, padded_work
+from sylber_b200.thresholder import Thresholder
+from oracle import frontdoor_ref
+
+REF = "/root/reference"
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_bucket_plan_is_a_partition_within_ratio(seed):
+    rng = np.random.default_rng(seed)
+    lengths = rng.integers(32000, 480001, size=97).tolist()
+    for ratio, max_batch in ((1.25, 64), (1.0, 8), (2.0, 5)):
+        buckets = plan_length_buckets(lengths, ratio, max_batch)
+        flat = sorted(i for b in buckets for i in b)
+        assert flat == list(range(len(lengths)))
+        for b in buckets:
+            assert 1 <= len(b) <= max_batch and b == sorted(b)
+            ls = [lengths[i] for i in b]
+            assert max(ls) <= min(ls) * ratio + 1e-9
+        assert plan_length_buckets(lengths, ratio, max_batch) == buckets       # deterministic
+        assert padded_work(lengths, buckets) <= padded_work(lengths)
+    # config 5's distribution (2-30 s): bucketing removes most of the padding
+    assert padded_work(lengths, plan_length_buckets(lengths, 1.25, 64)) < 0.75 * padded_work(lengths)
+
+
+def test_bucket_plan_edge_cases():
+    assert plan_length_buckets([], 1.25, 4) == []
+    assert plan_length_buckets([5], 1.25, 4) == [[0]]
+    assert plan_length_buckets([10, 10, 10], 1.0, 2) == [[0, 1], [2]]
+    with pytest.raises(ValueError):
+        plan_length_buckets([1, 2], 0.5, 4)
+
+
+# known answers computed with the unmodified reference class (torch 2.11, float32), see the test below
+THRESHOLD_CASES = [
+    ((8.0, 4.0, 1.5, 0.25), 3.0015573501586914),
+    ((6.5, 9.0, 2.0, 1.0), 3.7439115047454834),
+    ((3.0, 1.0, 1.0, 1.0), 2.0),
+    ((3.0, 2.0, 1.0, 1.0), 2.063706159591675),
+]
+
+
+def test_thresholder_known_answers():
+    for (sm, sv, nm, nv), want in THRESHOLD_CASES:
+        got = Thresholder(sm, sv, nm, nv).get_threshold()
+        assert abs(float(got) - want) <= 2e-6 * abs(want), (sm, sv, nm, nv, got, want)
+    assert float(Thresholder(threshold=2.6).get_threshold()) == pytest.approx(2.6, rel=1e-7)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present on this box")
+def test_thresholder_matches_reference_class():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_segment_utils", os.path.join(REF, "sylber/utils/segment_utils.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    RefThresholder = mod.Thresholder
+    rng = np.random.default_rng(0)
+    for (sm, sv, nm, nv), want in THRESHOLD_CASES:
+        ref = RefThresholder(sm, sv, nm, nv, decay=0.99)
+        ours = Thresholder(sm, sv, nm, nv, decay=0.99)
+        assert float(ref.get_threshold()) == pytest.approx(want, rel=1e-6)
+        for _ in range(5):
+            sig = rng.normal(sm, 2.0, size=300).astype(np.float32)
+            noi = rng.normal(nm, 0.5, size=200).astype(np.float32)
+            ref.update_stats(torch.from_numpy(sig), torch.from_numpy(noi))
+            ours.update_stats(sig, noi)
+            assert float(ours.get_threshold()) == pytest.approx(float(ref.get_threshold()), rel=2e-6)
+            assert float(ours.signal_var) == pytest.approx(float(ref.signal_var), rel=1e-6)
+
+
+def test_normalize_pcm16_oracle_follows_reference_lines():
+    rng = np.random.default_rng(3)
+    pcm = [(rng.normal(0, 3000, size=n)).astype(np.int16) for n in (16000, 9000)]
+    out, lens = frontdoor_ref.normalize_pcm16(pcm)
+    assert lens == [16000, 9000] and out.shape == (2, 16000)
+    for i, x in enumerate(pcm):
+        w = torch.from_numpy(x.astype(np.float32) / 32768.0)[None]          # torchaudio.load of 16-bit PCM
+        w = (w - w.mean()) / w.std()                                        # sylber.py:86
+        assert torch.equal(out[i, :lens[i]], w[0])
+        assert float(out[i, lens[i]:].abs().sum()) == 0.0
+        assert abs(float(out[i, :lens[i]].mean())) < 1e-5 and float(out[i, :lens[i]].std()) == pytest.approx(1.0, abs=1e-5)
+
+
+def test_kmeans_oracle_matches_brute_force():
+    rng = np.random.default_rng(4)
+    c = rng.normal(size=(50, 768)).astype(np.float32)
+    x = rng.normal(size=(20, 768)).astype(np.float32)
+    idx, _ = frontdoor_ref.kmeans_assign(x, c)
+    brute = np.array([np.argmin(((xi[None].astype(np.float64) - c.astype(np.float64)) ** 2).sum(-1)) for xi in x])
+    assert np.array_equal(idx, brute)
+    idx_n, _ = frontdoor_ref.kmeans_assign(x * 3.0, c, normalize=True)
+    idx_n2, _ = frontdoor_ref.kmeans_assign(x * 7.0, c, normalize=True)
+    assert np.array_equal(idx_n, idx_n2)          # the normalisation removes the scale
