@@ -19,6 +19,7 @@
 #include "frontdoor.cuh"
 #include "gemm_tc.cuh"
 #include "gemm2_tc.cuh"
+#include "gemm3_tc.cuh"
 #include "posconv.cuh"
 #include "mma_probe.cuh"
 #include "segment.cuh"
@@ -67,7 +68,7 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// tiled tensor map of up to 3 dims; elem_bytes 2 (fp16) or 4 (fp32); swizzle_bytes 128 or 64; box = {box0, box1, 1}
+// tiled tensor map of up to 3 dims; elem_bytes 2 (fp16) or 4 (fp32); swizzle_bytes 128, 64 or 0 (none); box = {box0, box1, 1}
 bool make_tmap(CUtensorMap* map, const void* base, int elem_bytes, int rank, const uint64_t* dims,
                const uint64_t* strides_elems, uint32_t box0, uint32_t box1, int swizzle_bytes, std::string* err) {
   EncodeTiledFn fn = get_encode_fn();
@@ -83,7 +84,8 @@ bool make_tmap(CUtensorMap* map, const void* base, int elem_bytes, int rank, con
   for (int i = 1; i < rank; ++i) gstr[i - 1] = strides_elems[i] * (uint64_t)elem_bytes;
   CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
                   const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
@@ -228,7 +230,8 @@ struct LayerW {
 
 struct GemmOp {
   CUtensorMap a_hi, a_lo;
-  CUtensorMap o_f32, o_hi, o_lo;
+  CUtensorMap o_f32, o_hi, o_lo;        // gemm_tc / gemm2_tc: {32, 32} boxes
+  CUtensorMap o3_f32, o3_hi, o3_lo;     // gemm3_tc: fp32 {16, 32} SWIZZLE_64B; fp16 {32, 32} SWIZZLE_64B (hi only) or {16, 32} plain
   const PackedLinear* w = nullptr;
   GemmParams p;
 };
@@ -502,6 +505,17 @@ bool make_o_maps(syl_handle* h, GemmOp& op, float* f32, __half* hi, __half* lo, 
   if (f32 && !make_out_map(&op.o_f32, f32, 4, ld, rows, nb, &h->err)) return false;
   if (hi && !make_out_map(&op.o_hi, hi, 2, ld, rows, nb, &h->err)) return false;
   if (lo && !make_out_map(&op.o_lo, lo, 2, ld, rows, nb, &h->err)) return false;
+  memset(&op.o3_f32, 0, sizeof(CUtensorMap));
+  memset(&op.o3_hi, 0, sizeof(CUtensorMap));
+  memset(&op.o3_lo, 0, sizeof(CUtensorMap));
+  {
+    uint64_t dims[3] = {(uint64_t)ld, (uint64_t)rows, (uint64_t)nb};
+    uint64_t str[3] = {1, (uint64_t)ld, (uint64_t)rows * ld};
+    const bool hi_wide = hi && !lo && !f32;
+    if (f32 && !make_tmap(&op.o3_f32, f32, 4, 3, dims, str, 16, 32, 64, &h->err)) return false;
+    if (hi && !make_tmap(&op.o3_hi, hi, 2, 3, dims, str, hi_wide ? 32 : 16, 32, hi_wide ? 64 : 0, &h->err)) return false;
+    if (lo && !make_tmap(&op.o3_lo, lo, 2, 3, dims, str, 16, 32, 0, &h->err)) return false;
+  }
   op.p.out_f32 = f32 != nullptr;
   op.p.out_hi = hi != nullptr;
   op.p.out_lo = lo != nullptr;
@@ -529,6 +543,26 @@ int launch_gemm2_raw(const GemmOp& op, const CUtensorMap& b_hi, const CUtensorMa
   return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
 }
 
+// 16-warp epilogue (gemm3_tc.cuh); SYL_GEMM_EPI16=0 falls back to the 8-warp gemm2 kernel for A/B timing
+bool gemm_use_epi16() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SYL_GEMM_EPI16");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+
+int launch_gemm3_raw(const GemmOp& op, const CUtensorMap& b_hi, const CUtensorMap& b_lo, cudaStream_t st, int sm_count) {
+  const GemmParams& p = op.p;
+  const int tiles_m = p.batches * ((p.rows_per_batch + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M));
+  const int tiles = tiles_m * (p.N / GEMM_BLOCK_N);
+  const int clusters = std::min(tiles, sm_count / 2);
+  if (clusters <= 0) return SYL_OK;
+  gemm3_tc_kernel<<<2 * clusters, GEMM3_THREADS, GEMM2_SMEM_TOTAL, st>>>(op.a_hi, op.a_lo, b_hi, b_lo, op.o3_f32, op.o3_hi, op.o3_lo, p);
+  return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
+}
+
 bool gemm_use_2cta() {
   static int v = -1;
   if (v < 0) {
@@ -540,8 +574,9 @@ bool gemm_use_2cta() {
 
 int launch_gemm(syl_handle* h, const GemmOp& op, cudaStream_t st, int sm_count) {
   if (gemm_use_2cta()) {
-    if (launch_gemm2_raw(op, op.w->map2_hi, op.w->map2_lo, st, sm_count) != SYL_OK)
-      return fail(h, SYL_E_CUDA, "gemm2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    const int rc = gemm_use_epi16() ? launch_gemm3_raw(op, op.w->map2_hi, op.w->map2_lo, st, sm_count)
+                                    : launch_gemm2_raw(op, op.w->map2_hi, op.w->map2_lo, st, sm_count);
+    if (rc != SYL_OK) return fail(h, SYL_E_CUDA, "gemm2/3 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     return SYL_OK;
   }
   if (launch_gemm_raw(op, op.w->map_hi, op.w->map_lo, st, sm_count) != SYL_OK)
@@ -563,6 +598,7 @@ int ensure_attrs(syl_handle* h) {
   if (g_attrs_set) return SYL_OK;
   CUDA_TRY(h, cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_TOTAL));
   CUDA_TRY(h, cudaFuncSetAttribute(gemm2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL));
+  CUDA_TRY(h, cudaFuncSetAttribute(gemm3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL));
   CUDA_TRY(h, cudaFuncSetAttribute(posconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM_TOTAL));
   CUDA_TRY(h, cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
   CUDA_TRY(h, (cudaFuncSetAttribute(attention7_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL)));
@@ -1306,6 +1342,12 @@ int syl_gemm_f32(const float* A, const float* W, const float* bias, const float*
   memset(&op.o_hi, 0, sizeof(CUtensorMap));
   memset(&op.o_lo, 0, sizeof(CUtensorMap));
   if (!make_out_map(&op.o_f32, out, 4, N, M, 1, &err)) return fail(nullptr, SYL_E_CUDA, "%s", err.c_str());
+  memset(&op.o3_hi, 0, sizeof(CUtensorMap));
+  memset(&op.o3_lo, 0, sizeof(CUtensorMap));
+  {
+    uint64_t od[3] = {(uint64_t)N, (uint64_t)M, 1}, os[3] = {1, (uint64_t)N, (uint64_t)M * N};
+    if (!make_tmap(&op.o3_f32, out, 4, 3, od, os, 16, 32, 64, &err)) return fail(nullptr, SYL_E_CUDA, "%s", err.c_str());
+  }
   op.p.rows_per_batch = M;
   op.p.batches = 1;
   op.p.N = N;
@@ -1323,7 +1365,9 @@ int syl_gemm_f32(const float* A, const float* W, const float* bias, const float*
     CUtensorMap b2_hi, b2_lo;
     if (!make_tmap_f16(&b2_hi, w_hi, 2, wd, wsd, 128, &err) || !make_tmap_f16(&b2_lo, w_lo, 2, wd, wsd, 128, &err))
       return fail(nullptr, SYL_E_CUDA, "%s", err.c_str());
-    if (launch_gemm2_raw(op, b2_hi, b2_lo, st, sms) != SYL_OK)
+    if (cudaFuncSetAttribute(gemm3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL) != cudaSuccess)
+      return fail(nullptr, SYL_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if ((gemm_use_epi16() ? launch_gemm3_raw(op, b2_hi, b2_lo, st, sms) : launch_gemm2_raw(op, b2_hi, b2_lo, st, sms)) != SYL_OK)
       return fail(nullptr, SYL_E_CUDA, "gemm2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   } else if (launch_gemm_raw(op, b_hi, b_lo, st, sms) != SYL_OK) {
     return fail(nullptr, SYL_E_CUDA, "gemm launch failed");

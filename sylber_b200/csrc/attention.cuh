@@ -404,10 +404,6 @@ constexpr int ATT7_SMEM_TOTAL = ATT_SMEM_BAR + 512 + 1024;      // 512 B of barr
 static_assert(ATT7_BAR_COUNT * 8 + 8 <= 512, "barrier block");
 static_assert(ATT_QT == 4, "two MMA threads x two tiles");
 
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-
 // exp2 on the FMA pipe for a pair of arguments (Cody-Waite split + degree-4 minimax polynomial on [-0.5, 0.5],
 // relative error 2.7e-6, far below the fp16 rounding of P).  Measured: no gain at 1 pair in 4, slower at 2 in 4 -
 // the softmax warps are bound by issue/latency, not by the MUFU (45 % busy) - so the default is 0 pairs; the switch

@@ -1,0 +1,286 @@
+// gemm2_tc_kernel with SIXTEEN epilogue warps (640 threads): same producer, MMA issuer, tiles and shared-memory
+// budget, but four epilogue warps per scheduler instead of two.  With K = 768 (12 k-blocks, ~6 100 tensor cycles per
+// tile) the 8-warp epilogue - two warps per scheduler walking 128 columns each through dependent MUFU / convert /
+// store chains - took longer than the main loop: QKV ran at 77 %, FFN1 (GELU) at 61-72 % and the out-projection at
+// 50 % tensor-pipe activity (profiles/r02_ncu_summary.md).  Each warp now owns a [32 rows x 64 columns] block and
+// walks it in 16-column steps so that its state fits the 96 registers per thread of a 640-thread CTA.
+// Output staging stays 2 KB per warp: fp32 as {16 col, 32 row} boxes (64-byte rows, SWIZZLE_64B), fp16 hi-only as
+// {32, 32} boxes filled by two steps, fp16 hi + lo as unswizzled {16, 32} boxes (1 KB each).
+#pragma once
+
+#include "gemm2_tc.cuh"
+
+namespace syl {
+
+constexpr int GEMM3_EPI_WARPS = 16;
+constexpr int GEMM3_THREADS = (GEMM_EPI_WARP0 + GEMM3_EPI_WARPS) * 32;   // 640
+constexpr int GEMM3_EPI_STAGE_BYTES = 2048;
+static_assert(GEMM3_EPI_WARPS * GEMM3_EPI_STAGE_BYTES == GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES, "same staging area as gemm2");
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM3_THREADS, 1)
+gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__ CUtensorMap a_lo,
+               const __grid_constant__ CUtensorMap b_hi, const __grid_constant__ CUtensorMap b_lo,
+               const __grid_constant__ CUtensorMap o_f32, const __grid_constant__ CUtensorMap o_hi,
+               const __grid_constant__ CUtensorMap o_lo, const GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();   // SWIZZLE_128B tiles need 1024-byte aligned stage buffers
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + GEMM2_STAGES * GEMM2_A_BYTES;
+  uint8_t* smem_epi = smem + GEMM2_SMEM_EPI;   // same 32 KB as gemm2: 16 warps x 2 KB
+  float* smem_bias = reinterpret_cast<float*>(smem + GEMM2_SMEM_BIAS);   // [2][256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM2_SMEM_BAR);
+  uint64_t* full_bar = bars;                           // [STAGES]  (used in the leader CTA)
+  uint64_t* empty_bar = bars + GEMM2_STAGES;           // [STAGES]  per CTA
+  uint64_t* tmem_full = bars + 2 * GEMM2_STAGES;       // [2]       per CTA
+  uint64_t* tmem_empty = bars + 2 * GEMM2_STAGES + 2;  // [2]       (used in the leader CTA)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * GEMM2_STAGES + 4);
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+
+  const int warp = threadIdx.x >> 5;
+  const int tiles_m_per_batch = (p.rows_per_batch + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);   // 256-row cluster tiles
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int tiles_n = p.N / GEMM_BLOCK_N;
+  const int num_tiles = p.batches * tiles_m_per_batch * tiles_n;
+  const int kb_total = p.kb_per_pass * p.n_pass;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&a_hi);
+    tma_prefetch_desc(&b_hi);
+    if (p.n_pass > 1) {
+      tma_prefetch_desc(&a_lo);
+      tma_prefetch_desc(&b_lo);
+    }
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < GEMM2_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);            // the leader's arrive.expect_tx; both CTAs' TMA bytes complete_tx on it
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * GEMM3_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2cta<GEMM_TMEM_COLS>(tmem_ptr);
+  }
+  tc_fence_before_sync();
+  cluster_sync_all();                        // barriers of both CTAs are initialised before anyone touches them
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int n_tile = tile % tiles_n;
+        const int m_tile = tile / tiles_n;
+        const int batch = m_tile / tiles_m_per_batch;
+        const int row0 = (m_tile % tiles_m_per_batch) * 2 * GEMM_BLOCK_M + (int)cta_rank * GEMM_BLOCK_M;
+        for (int kb = 0; kb < kb_total; ++kb) {
+          const int pass = kb / p.kb_per_pass;
+          const int kk = kb - pass * p.kb_per_pass;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * GEMM2_STAGE_BYTES);   // bytes of BOTH CTAs' loads
+          tma_load_3d_2sm(smem_a + stage * GEMM2_A_BYTES, (pass == 1) ? &a_lo : &a_hi, full_leader,
+                          kk * GEMM_BLOCK_K, row0, batch);
+          tma_load_2d_2sm(smem_b + stage * GEMM2_B_BYTES, (pass == 2) ? &b_lo : &b_hi, full_leader,
+                          kk * GEMM_BLOCK_K, n_tile * GEMM_BLOCK_N + (int)cta_rank * 128);
+          if (++stage == GEMM2_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_f16(2 * GEMM_BLOCK_M, GEMM_BLOCK_N, 0, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t tmem_d = tmem_base + acc * GEMM_BLOCK_N;
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint64_t adesc = make_desc_k_sw128(smem_u32(smem_a + stage * GEMM2_A_BYTES));
+          const uint64_t bdesc = make_desc_k_sw128(smem_u32(smem_b + stage * GEMM2_B_BYTES));
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+            // advancing K by 16 fp16 = 32 bytes inside the 128B swizzle row: +2 in 16-byte units
+            umma_f16_ss_2cta(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit_2cta(&empty_bar[stage]);  // frees this smem stage in both CTAs once the MMAs have read it
+          if (++stage == GEMM2_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2cta(&tmem_full[acc]);  // accumulator complete -> epilogue warps of both CTAs
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= GEMM_EPI_WARP0) {
+    // ------------------------------------------------------------------ epilogue
+    // 16 epilogue warps: warp (quarter, cb) owns TMEM lanes [32 quarter, +32) x columns [64 cb, +64) of the tile and
+    // walks them in four steps of 16 columns (double buffered tcgen05.ld.x16), so that the whole epilogue state fits
+    // the 96 registers a 640-thread CTA leaves per thread.
+    const int ew = warp - GEMM_EPI_WARP0;
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int cb = ew >> 2;                  // which 64-column block of the tile
+    const int lane = (int)lane_id();
+    const int epi_tid = threadIdx.x - GEMM_EPI_WARP0 * 32;   // 0..511
+    uint8_t* stage_buf = smem_epi + ew * GEMM3_EPI_STAGE_BYTES;      // 2 KB
+    const uint32_t stage_u32 = smem_u32(stage_buf);
+    const int sw64 = (lane >> 1) & 3;        // 64-byte rows, SWIZZLE_64B: 16-byte chunk index ^ ((row >> 1) & 3)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int it = 0;
+    // the staging buffer may be overwritten once the previous bulk store has finished reading it
+    auto acquire = [&]() {
+      if (lane == 0) tma_store_wait_read();
+      __syncwarp();
+    };
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      const int n_tile = tile % tiles_n;
+      const int m_tile = tile / tiles_n;
+      const int batch = m_tile / tiles_m_per_batch;
+      const int warp_row0 = (m_tile % tiles_m_per_batch) * 2 * GEMM_BLOCK_M + (int)cta_rank * GEMM_BLOCK_M + quarter * 32;
+      const int row_in_batch = warp_row0 + lane;
+      const bool warp_ok = warp_row0 < p.rows_per_batch;
+      const bool zero_row = p.valid_rows != nullptr && row_in_batch >= __ldg(p.valid_rows + batch);
+      const float scale = (n_tile * GEMM_BLOCK_N < p.col_scale_limit) ? p.col_scale : 1.0f;
+      // stage this tile's bias (pre-multiplied by the column scale, a power of two) in shared memory, double
+      // buffered by tile parity
+      float* sbias = smem_bias + (it & 1) * GEMM_BLOCK_N;
+      if (epi_tid < GEMM_BLOCK_N) sbias[epi_tid] = p.bias ? __ldg(p.bias + n_tile * GEMM_BLOCK_N + epi_tid) * scale : 0.0f;
+      named_bar_sync(1, GEMM3_EPI_WARPS * 32);
+      const f32x2 scale2 = pack2(scale, scale);
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * GEMM_BLOCK_N + cb * 64);
+      uint32_t r[2][16];
+      tmem_ld_32x32b_x16(taddr0, r[0]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        if (s + 1 < 4) tmem_ld_32x32b_x16(taddr0 + (s + 1) * 16, r[(s + 1) & 1]);   // prefetch the next 16 columns
+        const int col0 = n_tile * GEMM_BLOCK_N + cb * 64 + s * 16;
+        float v[16];
+        const float4* b4 = reinterpret_cast<const float4*>(sbias + cb * 64 + s * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 bb = b4[i];
+          // (acc + bias) * scale == acc * scale + bias * scale exactly: scale is a power of two
+          unpack2(fma2(pack2(__uint_as_float(r[s & 1][4 * i + 0]), __uint_as_float(r[s & 1][4 * i + 1])), scale2, pack2(bb.x, bb.y)),
+                  v[4 * i + 0], v[4 * i + 1]);
+          unpack2(fma2(pack2(__uint_as_float(r[s & 1][4 * i + 2]), __uint_as_float(r[s & 1][4 * i + 3])), scale2, pack2(bb.z, bb.w)),
+                  v[4 * i + 2], v[4 * i + 3]);
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gelu_fast2(v[2 * i], v[2 * i + 1], v[2 * i], v[2 * i + 1]);
+        }
+        if (zero_row) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0.0f;
+        }
+        if (warp_ok) {
+          if (p.out_f32) {
+            // 16 fp32 columns = 64-byte rows, 2 KB: box {16, 32}, SWIZZLE_64B
+            acquire();
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              st_shared_v4(stage_u32 + lane * 64 + ((i ^ sw64) << 4), __float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]),
+                           __float_as_uint(v[4 * i + 2]), __float_as_uint(v[4 * i + 3]));
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&o_f32, stage_buf, col0, warp_row0, batch);
+              tma_store_commit();
+            }
+          }
+          if (p.out_hi && !p.out_lo && !p.out_f32) {
+            // hi only: two steps fill 64-byte rows of 32 fp16 columns (2 KB), one bulk store {32, 32}, SWIZZLE_64B
+            uint32_t hi[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hi[i] = pack_f16x2_sat(v[2 * i], v[2 * i + 1]);
+            if ((s & 1) == 0) acquire();
+            const int c0 = (s & 1) * 2;                        // 16-byte chunk of the 64-byte row
+            st_shared_v4(stage_u32 + lane * 64 + (((c0 + 0) ^ sw64) << 4), hi[0], hi[1], hi[2], hi[3]);
+            st_shared_v4(stage_u32 + lane * 64 + (((c0 + 1) ^ sw64) << 4), hi[4], hi[5], hi[6], hi[7]);
+            if ((s & 1) == 1) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_3d(&o_hi, stage_buf, col0 - 16, warp_row0, batch);
+                tma_store_commit();
+              }
+            }
+          } else if (p.out_hi) {
+            // hi (+ lo) next to another destination: 16 columns = 32-byte rows, 1 KB (+ 1 KB), unswizzled boxes {16, 32}
+            uint32_t hi[8], lo[8];
+            if (p.out_lo) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) split_pair(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) hi[i] = pack_f16x2_sat(v[2 * i], v[2 * i + 1]);
+            }
+            acquire();
+            st_shared_v4(stage_u32 + lane * 32, hi[0], hi[1], hi[2], hi[3]);
+            st_shared_v4(stage_u32 + lane * 32 + 16, hi[4], hi[5], hi[6], hi[7]);
+            if (p.out_lo) {
+              st_shared_v4(stage_u32 + 1024 + lane * 32, lo[0], lo[1], lo[2], lo[3]);
+              st_shared_v4(stage_u32 + 1024 + lane * 32 + 16, lo[4], lo[5], lo[6], lo[7]);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&o_hi, stage_buf, col0, warp_row0, batch);
+              if (p.out_lo) tma_store_3d(&o_lo, stage_buf + 1024, col0, warp_row0, batch);
+              tma_store_commit();
+            }
+          }
+        }
+        if (s + 1 < 4) tmem_ld_wait();
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (lane == 0) tma_store_wait_all();   // bulk stores must be complete before the CTA exits
+  }
+
+  tc_fence_before_sync();
+  cluster_sync_all();                        // neither CTA may exit (or free TMEM) while its peer still uses it
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc_2cta<GEMM_TMEM_COLS>(tmem_base);
+  }
+}
+
+
+}  // namespace syl
