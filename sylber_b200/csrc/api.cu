@@ -204,6 +204,36 @@ __global__ void powf_half_kernel(const float* __restrict__ x, float* __restrict_
   if (i < n) y[i] = powf_half(x[i]);
 }
 
+// Launch with the programmatic-dependent-launch attribute (common.cuh: every kernel launched this way waits for its
+// predecessor with griddepcontrol.wait after its own prologue).  Measured in round 2 (profiles/r02_bench_ab.md): the
+// device-resident step does not change beyond run-to-run noise (4.78-5.08 vs 4.86-4.94 ms), and the end-to-end path,
+// which keeps three prioritised sub-batch streams in flight, gets SLOWER (6.4 vs 5.8 ms): early-launched dependents
+// of one stream hold scheduling slots the other streams need.  Hence opt-in: SYL_PDL=1.
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SYL_PDL");
+    v = e ? atoi(e) : 0;
+  }
+  return v != 0;
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int grid_for(size_t n, int block = 256) { return (int)std::min<size_t>((n + block - 1) / block, 148 * 16); }
 
 // ------------------------------------------------------------------------------------------------
@@ -284,6 +314,7 @@ struct syl_handle {
   std::vector<void*> owned;
   // packed weights
   float* conv0_w = nullptr;
+  uint4* conv0_bfrag = nullptr;    // mma.sync B fragments of conv0 (frontend.cuh)
   float *gn_g = nullptr, *gn_b = nullptr;
   PackedLinear convw[6];
   float *fp_ln_g = nullptr, *fp_ln_b = nullptr;
@@ -539,7 +570,8 @@ int launch_gemm2_raw(const GemmOp& op, const CUtensorMap& b_hi, const CUtensorMa
   const int tiles = tiles_m * (p.N / GEMM_BLOCK_N);
   const int clusters = std::min(tiles, sm_count / 2);
   if (clusters <= 0) return SYL_OK;
-  gemm2_tc_kernel<<<2 * clusters, GEMM_THREADS, GEMM2_SMEM_TOTAL, st>>>(op.a_hi, op.a_lo, b_hi, b_lo, op.o_f32, op.o_hi, op.o_lo, p);
+  launch_pdl(gemm2_tc_kernel, dim3(2 * clusters), dim3(GEMM_THREADS), GEMM2_SMEM_TOTAL, st, op.a_hi, op.a_lo, b_hi, b_lo, op.o_f32,
+             op.o_hi, op.o_lo, p);
   return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
 }
 
@@ -559,7 +591,8 @@ int launch_gemm3_raw(const GemmOp& op, const CUtensorMap& b_hi, const CUtensorMa
   const int tiles = tiles_m * (p.N / GEMM_BLOCK_N);
   const int clusters = std::min(tiles, sm_count / 2);
   if (clusters <= 0) return SYL_OK;
-  gemm3_tc_kernel<<<2 * clusters, GEMM3_THREADS, GEMM2_SMEM_TOTAL, st>>>(op.a_hi, op.a_lo, b_hi, b_lo, op.o3_f32, op.o3_hi, op.o3_lo, p);
+  launch_pdl(gemm3_tc_kernel, dim3(2 * clusters), dim3(GEMM3_THREADS), GEMM2_SMEM_TOTAL, st, op.a_hi, op.a_lo, b_hi, b_lo, op.o3_f32,
+             op.o3_hi, op.o3_lo, p);
   return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
 }
 
@@ -587,8 +620,8 @@ int launch_gemm(syl_handle* h, const GemmOp& op, cudaStream_t st, int sm_count) 
 int launch_posconv(syl_handle* h, const PosOp& op, cudaStream_t st, int sm_count) {
   const int t_tiles = (op.p.T + PC_TILE_T - 1) / PC_TILE_T;
   const int tiles = op.p.batches * t_tiles * PC_GROUPS;
-  posconv_kernel<<<std::min(tiles, sm_count), PC_THREADS, PC_SMEM_TOTAL, st>>>(op.a_hi, op.a_lo, h->pos.map_hi, h->pos.map_lo,
-                                                                             op.o_map, op.p);
+  launch_pdl(posconv_kernel, dim3(std::min(tiles, sm_count)), dim3(PC_THREADS), PC_SMEM_TOTAL, st, op.a_hi, op.a_lo, h->pos.map_hi,
+             h->pos.map_lo, op.o_map, op.p);
   CUDA_TRY(h, cudaGetLastError());
   return SYL_OK;
 }
@@ -759,7 +792,7 @@ template <int D>
 void launch_ln(const float* x, const float* add, const float* g, const float* b, int rows, float* of, __half* ohi,
                __half* olo, cudaStream_t st) {
   const int warps = 8;
-  layernorm_rows_kernel<D><<<(rows + warps - 1) / warps, warps * 32, 0, st>>>(x, add, g, b, rows, of, ohi, olo);
+  launch_pdl(layernorm_rows_kernel<D>, dim3((rows + warps - 1) / warps), dim3(warps * 32), 0, st, x, add, g, b, rows, of, ohi, olo);
 }
 
 long long* g_attn_trace = nullptr;   // set by syl_attention_trace for one launch
@@ -794,11 +827,11 @@ int launch_attention(const CUtensorMap& qkv, const CUtensorMap& o_hi, const CUte
   if (impl == 6)
     attention_kernel<<<grid, ATT_THREADS, ATT_SMEM_TOTAL, st>>>(qkv, o_hi, o_lo, ap);
   else if (ap.trace)
-    attention7_kernel<0, true><<<grid, ATT7_THREADS, ATT7_SMEM_TOTAL, st>>>(qkv, o_hi, o_lo, ap);
+    launch_pdl(attention7_kernel<0, true>, dim3(grid), dim3(ATT7_THREADS), ATT7_SMEM_TOTAL, st, qkv, o_hi, o_lo, ap);
   else if (poly == 1)
-    attention7_kernel<1, false><<<grid, ATT7_THREADS, ATT7_SMEM_TOTAL, st>>>(qkv, o_hi, o_lo, ap);
+    launch_pdl(attention7_kernel<1, false>, dim3(grid), dim3(ATT7_THREADS), ATT7_SMEM_TOTAL, st, qkv, o_hi, o_lo, ap);
   else
-    attention7_kernel<0, false><<<grid, ATT7_THREADS, ATT7_SMEM_TOTAL, st>>>(qkv, o_hi, o_lo, ap);
+    launch_pdl(attention7_kernel<0, false>, dim3(grid), dim3(ATT7_THREADS), ATT7_SMEM_TOTAL, st, qkv, o_hi, o_lo, ap);
   return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
 }
 
@@ -810,9 +843,9 @@ int run_frontend(syl_handle* h, const float* wav, cudaStream_t st) {
   {
     StageTimer tm(h, ST_CONV0, st);
     const int chunks = (L0 + MOM_T_PER_BLOCK - 1) / MOM_T_PER_BLOCK;
-    conv0_moments_kernel<<<dim3(chunks, B), MOM_THREADS, 0, st>>>(wav, pl.t_samp, L0, at<double>(ws, L.mom));
-    conv0_gn_coeff_kernel<<<B, kC, 0, st>>>(at<double>(ws, L.mom), chunks, h->conv0_w, h->gn_g, h->gn_b, L0,
-                                            at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift));
+    launch_pdl(conv0_moments_kernel, dim3(chunks, B), dim3(MOM_THREADS), 0, st, wav, pl.t_samp, L0, at<double>(ws, L.mom));
+    launch_pdl(conv0_gn_coeff_kernel, dim3(B), dim3(kC), 0, st, at<double>(ws, L.mom), chunks, h->conv0_w, h->gn_g, h->gn_b, L0,
+               at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift));
     __half* hi = at<__half>(ws, L.act_hi[0]);
     __half* lo = conv_split(h->mode, 1) ? at<__half>(ws, L.act_lo[0]) : nullptr;
     static int conv0_impl = -1;        // SYL_CONV0_IMPL=0: the FFMA kernel (kept for A/B timing), default: mma.sync
@@ -824,11 +857,11 @@ int run_frontend(syl_handle* h, const float* wav, cudaStream_t st) {
       conv0_apply_kernel<<<dim3((L0 + C0A_T - 1) / C0A_T, B), C0A_THREADS, 0, st>>>(
           wav, pl.t_samp, L0, h->conv0_w, at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift), hi, lo);
     else if (lo)
-      conv0_mma_kernel<true><<<dim3((L0 + C0M_T - 1) / C0M_T, B), C0M_THREADS, 0, st>>>(
-          wav, pl.t_samp, L0, h->conv0_w, at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift), hi, lo);
+      launch_pdl(conv0_mma_kernel<true>, dim3((L0 + C0M_T - 1) / C0M_T, B), dim3(C0M_THREADS), 0, st, wav, pl.t_samp, L0,
+                 h->conv0_bfrag, at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift), hi, lo);
     else
-      conv0_mma_kernel<false><<<dim3((L0 + C0M_T - 1) / C0M_T, B), C0M_THREADS, 0, st>>>(
-          wav, pl.t_samp, L0, h->conv0_w, at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift), hi, lo);
+      launch_pdl(conv0_mma_kernel<false>, dim3((L0 + C0M_T - 1) / C0M_T, B), dim3(C0M_THREADS), 0, st, wav, pl.t_samp, L0,
+                 h->conv0_bfrag, at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift), hi, lo);
   }
   CUDA_TRY(h, cudaGetLastError());
   {
@@ -891,9 +924,9 @@ int run_layer(syl_handle* h, int l, float* h_out, cudaStream_t st) {
 int run_segment(const float* states, int B, int T, float thr_norm, float thr_merge, int32_t* seg, int32_t* seg_count,
                 float* seg_feat, int max_seg, float* nsq, int32_t* scratch, cudaStream_t st) {
   const int rows = B * T;
-  frame_sqnorm_kernel<<<(rows + 7) / 8, 256, 0, st>>>(states, rows, nsq);
-  segment_kernel<<<B, 32, 0, st>>>(states, nsq, T, thr_norm, thr_merge, seg, seg_count, max_seg, scratch);
-  if (seg_feat) segment_pool_kernel<<<dim3(max_seg, B), 192, 0, st>>>(states, T, seg, seg_count, max_seg, seg_feat);
+  launch_pdl(frame_sqnorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, states, rows, nsq);
+  launch_pdl(segment_kernel, dim3(B), dim3(32), 0, st, states, nsq, T, thr_norm, thr_merge, seg, seg_count, max_seg, scratch);
+  if (seg_feat) launch_pdl(segment_pool_kernel, dim3(max_seg, B), dim3(192), 0, st, states, T, seg, seg_count, max_seg, seg_feat);
   return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
 }
 
@@ -984,6 +1017,8 @@ int syl_finalize(syl_handle* h) {
   if (rc) return rc;
   const std::string fe = "feature_extractor.conv_layers.";
   if (!(h->conv0_w = copy_vec(h, fe + "0.conv.weight", (size_t)kC * 10))) return SYL_E_STATE;
+  if (!(h->conv0_bfrag = dev_alloc<uint4>(h, 64 * 32))) return fail(h, SYL_E_CUDA, "cudaMalloc failed");
+  conv0_bfrag_kernel<<<8, 256>>>(h->conv0_w, h->conv0_bfrag);
   if (!(h->gn_g = copy_vec(h, fe + "0.layer_norm.weight", kC))) return SYL_E_STATE;
   if (!(h->gn_b = copy_vec(h, fe + "0.layer_norm.bias", kC))) return SYL_E_STATE;
   for (int i = 1; i <= 6; ++i) {

@@ -505,6 +505,7 @@ template <int kPolyPairs, bool kTrace>
 __global__ void __launch_bounds__(ATT7_THREADS, 1)
 attention7_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__ CUtensorMap o_hi,
                   const __grid_constant__ CUtensorMap o_lo, const AttnParams p) {
+  griddep_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_SMEM_BAR);
@@ -551,6 +552,7 @@ attention7_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_cons
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
+  griddep_wait();                  // QKV (and kv_len) written by the predecessor kernels are complete
   // timeline probe (kTrace builds only): writer 1 + x = lane 0 of warpgroup x's first warp, 5 + j = MMA thread j
   int trace_n = 0;
   auto trace = [&](int writer, int kind, int x, int u) {

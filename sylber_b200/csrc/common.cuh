@@ -130,6 +130,15 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// programmatic dependent launch: every kernel of the forward triggers its dependents at once and waits for its
+// predecessor only after its own prologue (barrier init, TMEM allocation, descriptor prefetch), so that prologue
+// and launch latency overlap the predecessor's tail.  Both are no-ops in a launch without the PDL attribute.
+// Rule kept by every kernel: NO global memory access (read or write) before griddep_wait().
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -29,6 +29,8 @@ constexpr int MOM_T_PER_BLOCK = 1024;
 
 __global__ void __launch_bounds__(MOM_THREADS)
 conv0_moments_kernel(const float* __restrict__ wav, int t_samp, int L0, double* __restrict__ part) {
+  griddep_launch_dependents();
+  griddep_wait();
   __shared__ float xs[MOM_T_PER_BLOCK * C0_S + C0_K];
   __shared__ double red[MOM_THREADS / 32][C0_NMOM];
   const int b = blockIdx.y;
@@ -74,6 +76,8 @@ conv0_moments_kernel(const float* __restrict__ wav, int t_samp, int L0, double* 
 __global__ void conv0_gn_coeff_kernel(const double* __restrict__ part, int chunks, const float* __restrict__ w0,
                                       const float* __restrict__ gamma, const float* __restrict__ beta, int L0,
                                       float* __restrict__ scale, float* __restrict__ shift) {
+  griddep_launch_dependents();
+  griddep_wait();
   __shared__ double m[C0_NMOM];
   const int b = blockIdx.x;
   const int c = threadIdx.x;
@@ -175,13 +179,14 @@ conv0_apply_kernel(const float* __restrict__ wav, int t_samp, int L0, const floa
 // and the fp16 conversion.  tcgen05 is not used here on purpose: K = 10 and one TMEM round trip per 512-channel row
 // would cost more than the MMA saves, while mma.sync keeps the accumulator in the registers the epilogue needs.
 //
-// grid (ceil(L0 / 256), B), block 128: warp w owns channels [128 w, 128 w + 128) of every frame of the block and
-// keeps the B fragments of its 16 channel octets in registers.  Inside a group of four octets the MMA columns are
-// permuted so that a lane ends up with 8 CONSECUTIVE channels per frame row, i.e. one 16-byte store:
+// grid (ceil(L0 / 256), B), block 256: warp w owns channels [128 (w & 3), + 128) of half of the block's frames; the B
+// fragments of the 64 channel octets come from a 32 KB table built at syl_finalize and read through L1.  Inside a group
+// of four octets the MMA columns are permuted so that a lane ends up with 8 CONSECUTIVE channels per frame row, i.e.
+// one 16-byte store:
 //     MMA column n of octet jj in group grp  <->  channel 128 w + 32 grp + 8 (n >> 1) + 2 jj + (n & 1)
 // ----------------------------------------------------------------------------------------------
-constexpr int C0M_THREADS = 128;
-constexpr int C0M_T = 256;       // frames per block = 16 frame tiles of 16
+constexpr int C0M_THREADS = 256;
+constexpr int C0M_T = 256;       // frames per block = 16 frame tiles of 16: warps 0-3 take tiles 0-7, warps 4-7 tiles 8-15
 
 __device__ __forceinline__ void mma_m16n8k16_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
@@ -189,14 +194,34 @@ __device__ __forceinline__ void mma_m16n8k16_f16(float (&c)[4], const uint32_t (
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// B fragments ("col" operand) of all 64 channel octets, built once at syl_finalize: tab[octet][lane] =
+// {hi(k = 2 tig, 2 tig + 1), hi(k = 2 tig + 8, + 9), lo(...), lo(...)} of MMA column n = lane >> 2, i.e. of channel
+// 128 w + 32 grp + 8 (n >> 1) + 2 jj + (n & 1) with octet = 16 w + 4 grp + jj; taps >= 10 are zero.  32 KB, read
+// through L1 by every block - keeping the fragments in registers cost 64 registers per thread and held the kernel
+// at 4 warps per scheduler.
+__global__ void conv0_bfrag_kernel(const float* __restrict__ w0, uint4* __restrict__ tab) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 32) return;
+  const int o = i >> 5, lane = i & 31, g = lane >> 2, tig = lane & 3;
+  const int ch = (o >> 4) * 128 + ((o >> 2) & 3) * 32 + (g >> 1) * 8 + (o & 3) * 2 + (g & 1);
+  const float* wc = w0 + ch * C0_K;
+  const float w10 = (tig == 0) ? wc[8] : 0.0f, w11 = (tig == 0) ? wc[9] : 0.0f;
+  uint4 v;
+  split_pair(wc[2 * tig], wc[2 * tig + 1], v.x, v.z);
+  split_pair(w10, w11, v.y, v.w);
+  tab[i] = v;
+}
+
 template <bool kLo>
 __global__ void __launch_bounds__(C0M_THREADS, 4)
-conv0_mma_kernel(const float* __restrict__ wav, int t_samp, int L0, const float* __restrict__ w0,
+conv0_mma_kernel(const float* __restrict__ wav, int t_samp, int L0, const uint4* __restrict__ bfrag,
                  const float* __restrict__ scale, const float* __restrict__ shift, __half* __restrict__ out_hi,
                  __half* __restrict__ out_lo) {
   __shared__ float xs[C0M_T * C0_S + 16];
   __shared__ __align__(16) float s_sc[C0_OUT];
   __shared__ __align__(16) float s_sh[C0_OUT];
+  griddep_launch_dependents();
+  griddep_wait();
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * C0M_T;
   const int nt = min(C0M_T, L0 - t0);
@@ -208,23 +233,13 @@ conv0_mma_kernel(const float* __restrict__ wav, int t_samp, int L0, const float*
     s_sh[i] = shift[b * C0_OUT + i];
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slab = warp & 3, half = warp >> 2;
   const int g = lane >> 2, tig = lane & 3;
-  // B fragments (weights, "col" operand): this lane holds column n = g of every octet, k = 2 tig, 2 tig + 1 (b0) and
-  // k = 2 tig + 8, 2 tig + 9 (b1); taps >= 10 are zero
-  uint32_t bh[16][2], bl[16][2];
-#pragma unroll
-  for (int o = 0; o < 16; ++o) {
-    const int ch = warp * 128 + (o >> 2) * 32 + (g >> 1) * 8 + (o & 3) * 2 + (g & 1);
-    const float* wc = w0 + ch * C0_K;
-    const float w00 = wc[2 * tig], w01 = wc[2 * tig + 1];
-    const float w10 = (tig == 0) ? wc[8] : 0.0f, w11 = (tig == 0) ? wc[9] : 0.0f;
-    split_pair(w00, w01, bh[o][0], bl[o][0]);
-    split_pair(w10, w11, bh[o][1], bl[o][1]);
-  }
+  const uint4* btab = bfrag + (size_t)slab * 16 * 32 + lane;
   __syncthreads();
 
-  const int ch0 = warp * 128 + tig * 8;         // + 32 grp: the 8 consecutive channels of this lane in group grp
-  for (int ft = 0; ft < C0M_T / 16; ++ft) {
+  const int ch0 = slab * 128 + tig * 8;         // + 32 grp: the 8 consecutive channels of this lane in group grp
+  for (int ft = half * 8; ft < half * 8 + 8; ++ft) {
     if (ft * 16 >= nt) break;
     // A fragments (waveform windows, row-major 16 x 16): rows g and g + 8, k as for B
     uint32_t ah[4], al[4];
@@ -252,11 +267,11 @@ conv0_mma_kernel(const float* __restrict__ wav, int t_samp, int L0, const float*
       uint32_t h0[4], h1[4], l0[4], l1[4];
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
-        const int o = grp * 4 + jj;
+        const uint4 bf = __ldg(btab + (grp * 4 + jj) * 32);     // {hi0, hi1, lo0, lo1}
         float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        mma_m16n8k16_f16(c, al, bh[o][0], bh[o][1]);     // small terms first
-        mma_m16n8k16_f16(c, ah, bl[o][0], bl[o][1]);
-        mma_m16n8k16_f16(c, ah, bh[o][0], bh[o][1]);
+        mma_m16n8k16_f16(c, al, bf.x, bf.y);     // small terms first
+        mma_m16n8k16_f16(c, ah, bf.z, bf.w);
+        mma_m16n8k16_f16(c, ah, bf.x, bf.y);
         // c[0], c[1]: row g, channels ch0 + 32 grp + 2 jj + {0, 1};  c[2], c[3]: row g + 8, same channels
         const f32x2 sc2 = pack2(scv[2 * jj], scv[2 * jj + 1]), sh2 = pack2(shv[2 * jj], shv[2 * jj + 1]);
         float y0, y1, y2, y3;
@@ -294,6 +309,8 @@ layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ add
                       const float* __restrict__ beta, int rows, float* __restrict__ out_f32,
                       __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
   constexpr int V = D / 128;  // float4 per lane
+  griddep_launch_dependents();
+  griddep_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = lane_id();

@@ -99,6 +99,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
                const __grid_constant__ CUtensorMap b_hi, const __grid_constant__ CUtensorMap b_lo,
                const __grid_constant__ CUtensorMap o_f32, const __grid_constant__ CUtensorMap o_hi,
                const __grid_constant__ CUtensorMap o_lo, const GemmParams p) {
+  griddep_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // SWIZZLE_128B tiles need 1024-byte aligned stage buffers
@@ -149,6 +150,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
   cluster_sync_all();                        // barriers of both CTAs are initialised before anyone touches them
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
+  griddep_wait();                            // the predecessor kernel's output (our A operand, valid_rows) is complete
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer

@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(PC_THREADS, 1)
 posconv_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__ CUtensorMap a_lo,
                const __grid_constant__ CUtensorMap w_hi, const __grid_constant__ CUtensorMap w_lo,
                const __grid_constant__ CUtensorMap o_map, const PosConvParams p) {
+  griddep_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PC_SMEM_BAR);
@@ -96,6 +97,7 @@ posconv_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
+  griddep_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer

@@ -110,6 +110,8 @@ __device__ __forceinline__ float np_sum_serial(const float* a, int n) { return _
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 frame_sqnorm_kernel(const float* __restrict__ states, int rows, float* __restrict__ nsq) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = lane_id();
@@ -148,6 +150,8 @@ __global__ void __launch_bounds__(32)
 segment_kernel(const float* __restrict__ states_all, const float* __restrict__ nsq_all, int T, float thr_norm,
                float thr_merge, int32_t* __restrict__ seg_all, int32_t* __restrict__ seg_count, int max_seg,
                int32_t* __restrict__ scratch_all) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int b = blockIdx.x;
   const int lane = lane_id();
   const float* states = states_all + (size_t)b * T * SEG_D;
@@ -294,6 +298,8 @@ segment_kernel(const float* __restrict__ states_all, const float* __restrict__ n
 __global__ void __launch_bounds__(192)
 segment_pool_kernel(const float* __restrict__ states_all, int T, const int32_t* __restrict__ seg_all,
                     const int32_t* __restrict__ seg_count, int max_seg, float* __restrict__ feat_all) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int b = blockIdx.y, sidx = blockIdx.x;
   if (sidx >= min(seg_count[b], max_seg)) return;
   const int s = seg_all[((size_t)b * max_seg + sidx) * 2], e = seg_all[((size_t)b * max_seg + sidx) * 2 + 1];
