@@ -379,6 +379,7 @@ class Segmenter:
         mode = kwargs.pop("mode", "parity")
         self.max_batch = int(kwargs.pop("max_batch", 64))
         self.streams = int(kwargs.pop("streams", 3))
+        self.sub_batch_sizes = kwargs.pop("sub_batch_sizes", None)
         self.bucket_ratio = kwargs.pop("bucket_ratio", None)       # e.g. 1.25: length-bucketed batching (batching.py)
         self.thresholder = kwargs.pop("thresholder", None)         # sylber_b200.Thresholder for segment(normthreshold=None)
         self.enc_dim = HIDDEN
@@ -437,10 +438,26 @@ class Segmenter:
         n_rows = len(rows)
         n_sub = max(1, min(self.streams, n_rows // 8)) if n_rows <= self.max_batch else 1
         bounds = []
-        for lo in range(0, n_rows, self.max_batch):
-            hi = min(lo + self.max_batch, n_rows)
-            step = -(-(hi - lo) // n_sub)
-            bounds += [(a, min(a + step, hi)) for a in range(lo, hi, step)]
+        if self.sub_batch_sizes and sum(self.sub_batch_sizes) == n_rows:       # explicit split (experiments)
+            a = 0
+            for k in self.sub_batch_sizes:
+                bounds.append((a, a + k))
+                a += k
+            n_sub = min(self.streams, len(bounds))
+        else:
+            for lo in range(0, n_rows, self.max_batch):
+                hi = min(lo + self.max_batch, n_rows)
+                # the LAST sub-batch's device->host copy is the one nothing overlaps, so it gets 2/3 of an even share
+                # (32 rows, 3 streams -> 12, 12, 8: measured 6.08 ms against 6.40 ms for 11, 11, 10)
+                n = hi - lo
+                sizes = [int(round(n / (n_sub - 1 / 3)))] * (n_sub - 1) if n_sub > 1 else []
+                sizes.append(n - sum(sizes))
+                if min(sizes) <= 0:
+                    sizes = [n]
+                a = lo
+                for k in sizes:
+                    bounds.append((a, a + k))
+                    a += k
         # always a side stream, even for one sub-batch: the legacy default stream cannot be graph-captured
         streams = eng.side_streams(n_sub)
         main = torch.cuda.current_stream(eng.device)

@@ -1,0 +1,17 @@
+"""End-to-end time of Segmenter.__call__ (32 x 10 s, pinned inputs) for different sub-batch splits."""
+import sys, time, torch
+sys.path.insert(0, ".")
+from sylber_b200 import Segmenter
+from sylber_b200.weights import syllabic_test_state_dict
+sd = syllabic_test_state_dict(9, 0)
+g = torch.Generator().manual_seed(1)
+wav = torch.randn(32, 160000, generator=g).pin_memory()
+wl = [wav[i:i+1] for i in range(32)]
+for split in ([32], [16, 16], [11, 11, 10], [12, 12, 8], [14, 12, 6], [13, 10, 9], [8, 8, 8, 8], [10, 8, 8, 6], [12, 10, 6, 4], [16, 10, 6]):
+    seg = Segmenter(model_ckpt=None, state_dict=sd, device="cuda:0", streams=len(split), sub_batch_sizes=split, max_batch=32)
+    for _ in range(4): seg(wav=wl)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(20): r = seg(wav=wl)
+    torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 20
+    print("split", split, "e2e ms", round(dt * 1e3, 3), "frames/s", round(32 * 499 / dt), flush=True)
+    del seg
