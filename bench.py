@@ -159,17 +159,17 @@ def run_reference(args):
         return
     from sylber_b200.weights import syllabic_test_state_dict
     sd = syllabic_test_state_dict(args.layers, 0)
-    batch = 4
+    batch = 4 if N_SAMPLES <= 160000 else 1
     fps, ms = time_cpu(sd, args.layers, batch, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"batch=32 synthetic 10 s 16 kHz wav, sylber_base ({args.layers}L/768d)",
+        "config": {"workload": f"batch={BATCH_PER_GPU} synthetic {N_SAMPLES // 16000} s 16 kHz wav, sylber_base ({args.layers}L/768d)",
                    "note": "CPU path of the reference restated in oracle/ (torch CPU conv/linear/SDPA-equivalent ops + "
                            "NumPy get_segment); each step is a bounded sample of 4 clips of the workload"},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{batch} x 10 s clips per step, {args.steps} steps, torch {torch.__version__} fp32, "
+                         "sample": f"{batch} x {N_SAMPLES // 16000} s clips per step, {args.steps} steps, torch {torch.__version__} fp32, "
                                    f"os.cpu_count()={os.cpu_count()}"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -333,7 +333,7 @@ def run_ours(args):
     split_layers = {"fast": (), "parity": (4, 5, 6), "strict": (1, 2, 3, 4, 5, 6), "exact": (1, 2, 3, 4, 5, 6)}[args.mode]
     conv_eq = sum(f * (3 if i in split_layers else 1) for i, f in zip(range(1, 7), per_layer)) * B / (conv_ms * 1e-3) / 1e12
     roofline = {
-        "bound": "tensor", "kernel": "gemm3_tc_kernel", "launch": "conv1 implicit GEMM, M=32x15999 N=512 K=1536", "stage": dom,
+        "bound": "tensor", "kernel": "gemm3_tc_kernel", "launch": f"conv1 implicit GEMM, M={B}x{L[1]} N=512 K=1536", "stage": dom,
         "achieved": stages[dom]["achieved_tflops"], "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
         "frac": stages[dom]["frac"], "traffic": traffic,
         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); fp16 and bf16 share the tensor rate",
@@ -357,11 +357,11 @@ def run_ours(args):
                   "strict": " (conv1-6, projection, pos-conv split; 3.0e-4)", "exact": " (every GEMM split; 2.7e-5)",
                   "fast": " (no split; 5.5e-4)"}[args.mode],
         "data": "synthetic",
-        "config": {"workload": f"batch=32 synthetic 10 s 16 kHz wav per GPU, sylber_base ({layers}L/768d), 1xB200 per rank",
+        "config": {"workload": f"batch={B} synthetic {N_SAMPLES // 16000} s 16 kHz wav per GPU, sylber_base ({layers}L/768d), 1xB200 per rank",
                    "frames_per_clip": T, "batch_per_gpu": B, "mode": args.mode, "parallelism": f"dp{world} by utterance",
                    "l2": "per-step working set (~4 GB of activations) exceeds the 126 MB L2; no explicit flush",
                    "segments_per_clip_mean": float(seg_counts.mean()),
-                   "e2e_input": "list of 32 (1, 160000) fp32 views of one pinned host tensor",
+                   "e2e_input": f"list of {B} (1, {N_SAMPLES}) fp32 views of one pinned host tensor",
                    "variant_env": {k: v for k, v in os.environ.items() if k.startswith("SYL_")}},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / args.steps * 1e3},
@@ -374,9 +374,10 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu:
         torch.cuda.synchronize()
-        fps, ms = time_cpu(sd, layers, 8, 2, 1)
+        n_cpu = 8 if N_SAMPLES <= 160000 else 2
+        fps, ms = time_cpu(sd, layers, n_cpu, 2, 1)
         line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"8 x 10 s clips, 1 warm-up + 2 timed passes of oracle/ (torch CPU fp32 + NumPy "
+                                "sample": f"{n_cpu} x {N_SAMPLES // 16000} s clips, 1 warm-up + 2 timed passes of oracle/ (torch CPU fp32 + NumPy "
                                           f"get_segment), os.cpu_count()={os.cpu_count()}", "ms_per_step": ms}
     print(json.dumps(line))
     if world > 1:
@@ -393,7 +394,13 @@ def main():
     ap.add_argument("--mode", default="parity", choices=["parity", "strict", "fast", "exact"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--streams", type=int, default=0, help="sub-batches in flight in the e2e leg (0 = Segmenter default)")
+    ap.add_argument("--workload", default="10s", choices=["10s", "60s"],
+                    help="10s = BASELINE configs[1]/[2] (batch 32 x 10 s per GPU, the metric's configuration); "
+                         "60s = configs[3] (batch 8 x 60 s, T = 2999: the attention-roofline case)")
     args = ap.parse_args()
+    global N_SAMPLES, BATCH_PER_GPU
+    if args.workload == "60s":
+        N_SAMPLES, BATCH_PER_GPU = 960000, 8
     if args.impl == "reference":
         run_reference(args)
     else:

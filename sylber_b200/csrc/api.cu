@@ -282,6 +282,8 @@ struct WsLayout {
 
 struct Plan {
   bool valid = false;
+  uint64_t last_use = 0;   // LRU stamp
+  int uses = 0;            // forwards run with this plan: a CUDA graph is only captured from the second one on
   int batch = 0, t_samp = 0;
   void* ws = nullptr;
   float* hidden = nullptr;
@@ -322,9 +324,10 @@ struct syl_handle {
   PackedLinear pos;
   float *enc_ln_g = nullptr, *enc_ln_b = nullptr;
   std::vector<LayerW> layers;
-  Plan plans[4];       // small cache: callers that alternate between workspaces (sub-batch streams) keep their maps
+  static constexpr int kPlans = 16;   // LRU cache: sub-batch streams and length buckets alternate between shapes / workspaces
+  Plan plans[kPlans];
   int plan_cur = 0;
-  int plan_next = 0;
+  uint64_t plan_clock = 0;
   int sm_count = 148;
   bool profile = false;
   bool use_graphs = true;
@@ -654,17 +657,24 @@ int posconv_base_offset_mode() {
 // plan: tensor maps + GEMM parameters for one (batch, t_samp, workspace, hidden) combination
 // ------------------------------------------------------------------------------------------------
 int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
-  for (int i = 0; i < 4; ++i) {
-    const Plan& c = h->plans[i];
+  for (int i = 0; i < syl_handle::kPlans; ++i) {
+    Plan& c = h->plans[i];
     if (c.valid && c.batch == batch && c.t_samp == t_samp && c.ws == ws) {
       h->plan_cur = i;
+      c.last_use = ++h->plan_clock;
       return SYL_OK;
     }
   }
-  h->plan_cur = h->plan_next;
-  h->plan_next = (h->plan_next + 1) % 4;
+  int victim = 0;
+  for (int i = 0; i < syl_handle::kPlans; ++i) {
+    if (!h->plans[i].valid) { victim = i; break; }
+    if (h->plans[i].last_use < h->plans[victim].last_use) victim = i;
+  }
+  h->plan_cur = victim;
   Plan& pl = h->plans[h->plan_cur];
   pl.valid = false;
+  pl.uses = 0;
+  pl.last_use = ++h->plan_clock;
   for (auto& g : pl.graphs) cudaGraphExecDestroy(g.exec);
   pl.graphs.clear();
   pl.batch = batch;
@@ -1173,7 +1183,10 @@ int syl_forward(syl_handle* h, const float* wav, const int32_t* n_samples, int b
   // (2.8 ms of CPU per step, measured) and the launch gaps between the short kernels.  Graphs are keyed by the
   // full argument set; per-stage profiling needs real events, so it uses the eager path.
   // (the legacy default stream cannot be captured)
-  const bool graphs = h->use_graphs && !h->profile && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
+  // a shape seen for the first time runs eagerly: capturing + instantiating a graph costs more than one eager forward,
+  // and callers with ever-changing shapes (mixed-length lists, length buckets) would pay it on every call
+  const bool graphs = h->use_graphs && !h->profile && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread &&
+                      pl.uses++ > 0;
   if (graphs) {
     for (const Plan::GraphEntry& g : pl.graphs) {
       if (g.key[0] == wav && g.key[1] == n_samples && g.key[2] == hidden && g.key[3] == seg && g.key[4] == seg_count &&

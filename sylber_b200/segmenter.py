@@ -245,19 +245,23 @@ class _Engine:
         T = self.num_frames(t_samp)
         ws, need = self.workspace(B, t_samp, slot)
         max_seg = (T if max_seg is None else int(max_seg)) if segment else 0
-        # Output buffers are persistent per slot: stable pointers let the library replay its CUDA graph.
-        # They are overwritten by the next forward on the same slot - callers that keep results clone them.
+        # Output buffers are persistent per (slot, shape): stable pointers let the library replay its CUDA graph.
+        # They are overwritten by the next forward of the same slot and shape - callers that keep results clone them.
+        # A small LRU keeps the shapes of recurring length buckets alive.
         key = (slot, B, T, max_seg)
-        io = self._io.get(slot)
-        if io is None or io[0] != key:
+        io = self._io.pop(key, None)
+        if io is None:
             hidden = torch.empty((B, T, HIDDEN), dtype=torch.float32, device=self.device)
             seg = cnt = feat = None
             if segment:
                 seg = torch.empty((B, max_seg, 2), dtype=torch.int32, device=self.device)
                 cnt = torch.empty((B,), dtype=torch.int32, device=self.device)
                 feat = torch.empty((B, max_seg, HIDDEN), dtype=torch.float32, device=self.device)
-            io = self._io[slot] = (key, hidden, seg, cnt, feat)
-        _, hidden, seg, cnt, feat = io
+            io = (hidden, seg, cnt, feat)
+            while len(self._io) >= 12:
+                self._io.pop(next(iter(self._io)))
+        self._io[key] = io                       # most recently used last
+        hidden, seg, cnt, feat = io
         stream = torch.cuda.current_stream(self.device).cuda_stream
         rc = self.lib.syl_forward(self.handle, _ptr(wav), _ptr(n_samples), B, t_samp, _ptr(hidden), _ptr(seg), _ptr(cnt),
                                   _ptr(feat), max_seg, float(thr_norm), float(thr_merge),
@@ -429,13 +433,8 @@ class Segmenter:
         return batch_wavs, is_batch
 
     # ------------------------------------------------------------------------------------------
-    def _run_rows(self, rows, lengths, max_length, pcm=False):
-        """One padded batch through the engine.  rows: 1-D fp32 CPU tensors (or int16 when `pcm`), every row padded to
-        `max_length`.  Returns per row (segments int64 (N,2) | empty, segment_features (N,768) | empty, hidden)."""
-        eng = self._engine
-        # Sub-batches run on separate streams so that one sub-batch's host->device / device->host copies overlap the
-        # others' kernels.  Every sub-batch is padded to the batch-wide max_length: results depend on T_max (8a).
-        n_rows = len(rows)
+    def _sub_batches(self, n_rows):
+        """(lo, hi) sub-batch bounds of one padded batch of n_rows rows."""
         n_sub = max(1, min(self.streams, n_rows // 8)) if n_rows <= self.max_batch else 1
         bounds = []
         if self.sub_batch_sizes and sum(self.sub_batch_sizes) == n_rows:       # explicit split (experiments)
@@ -443,61 +442,86 @@ class Segmenter:
             for k in self.sub_batch_sizes:
                 bounds.append((a, a + k))
                 a += k
-            n_sub = min(self.streams, len(bounds))
-        else:
-            for lo in range(0, n_rows, self.max_batch):
-                hi = min(lo + self.max_batch, n_rows)
-                # the LAST sub-batch's device->host copy is the one nothing overlaps, so it gets 2/3 of an even share
-                # (32 rows, 3 streams -> 12, 12, 8: measured 6.08 ms against 6.40 ms for 11, 11, 10)
-                n = hi - lo
-                sizes = [int(round(n / (n_sub - 1 / 3)))] * (n_sub - 1) if n_sub > 1 else []
-                sizes.append(n - sum(sizes))
-                if min(sizes) <= 0:
-                    sizes = [n]
-                a = lo
-                for k in sizes:
-                    bounds.append((a, a + k))
-                    a += k
+            return bounds
+        for lo in range(0, n_rows, self.max_batch):
+            hi = min(lo + self.max_batch, n_rows)
+            # the LAST sub-batch's device->host copy is the one nothing overlaps, so it gets 2/3 of an even share
+            # (32 rows, 3 streams -> 12, 12, 8: measured 6.08 ms against 6.40 ms for 11, 11, 10)
+            n = hi - lo
+            sizes = [int(round(n / (n_sub - 1 / 3)))] * (n_sub - 1) if n_sub > 1 else []
+            sizes.append(n - sum(sizes))
+            if min(sizes) <= 0:
+                sizes = [n]
+            a = lo
+            for k in sizes:
+                bounds.append((a, a + k))
+                a += k
+        return bounds
+
+    def _run_jobs(self, rows, lengths, jobs, pcm=False):
+        """Padded batches through the engine.  rows: 1-D fp32 CPU tensors (or int16 when `pcm`); jobs: list of
+        (row indices, max_length) - every row of a job is padded to that job's max_length (results depend on it, 8a).
+        Returns per row (segments int64 (N,2) | empty, segment_features (N,768) | empty, hidden).
+
+        All sub-batches of all jobs are launched first, round-robin over the streams (a sub-batch's host->device /
+        device->host copies overlap the others' kernels), and collected afterwards."""
+        eng = self._engine
+        work = []
+        for idx, max_length in jobs:
+            for lo, hi in self._sub_batches(len(idx)):
+                work.append((idx[lo:hi], max_length))
         # always a side stream, even for one sub-batch: the legacy default stream cannot be graph-captured
-        streams = eng.side_streams(n_sub)
+        streams = eng.side_streams(max(1, min(self.streams, len(work))))
         main = torch.cuda.current_stream(eng.device)
         thr_n, thr_m = np.float32(self.norm_threshold), np.float32(self.merge_threshold)
-        pending = []
-        for k, (lo, hi) in enumerate(bounds):
-            slot = k % len(streams)
-            st = streams[slot]
-            chunk = rows[lo:hi]
-            if k >= len(streams):                      # this slot's staging buffer and workspace are about to be reused
-                st.synchronize()
-            st.wait_stream(main)
-            with torch.cuda.stream(st):
-                if pcm:
-                    wav_dev, n_dev = eng.upload_pcm16(chunk, lengths[lo:hi], max_length, slot)
-                else:
-                    wav_dev, n_dev = eng.upload(chunk, lengths[lo:hi], max_length, slot)
-                hidden, seg, cnt, feat = eng.forward(wav_dev, n_dev, thr_n, thr_m, slot=slot)
-                hidden_h, hidden_pin = eng.pool.array(tuple(hidden.shape))
-                hidden_pin.copy_(hidden, non_blocking=True)
-                cnt_pin = torch.empty(cnt.shape, dtype=torch.int32, pin_memory=True)
-                cnt_pin.copy_(cnt, non_blocking=True)
-            pending.append((st, lo, hi, hidden_h, hidden_pin, seg, cnt_pin, feat))
-        out = []
-        for st, lo, hi, hidden_h, hidden_pin, seg, cnt_pin, feat in pending:
+        results = [None] * len(rows)
+
+        def collect(item):
+            st, idx, hidden_h, hidden_pin, seg, cnt_pin, feat = item
             st.synchronize()
             cnt_h = cnt_pin.numpy()
             n_max = max(int(cnt_h.max()) if len(cnt_h) else 0, 1)
             with torch.cuda.stream(st):
                 seg_h = seg[:, :n_max].cpu().numpy()
-                feat_h, feat_pin = eng.pool.array((hi - lo, n_max, HIDDEN))
+                feat_h, feat_pin = eng.pool.array((len(idx), n_max, HIDDEN))
                 feat_pin.copy_(feat[:, :n_max], non_blocking=True)
             st.synchronize()
             del hidden_pin, feat_pin
-            for i in range(hi - lo):
+            for i, r in enumerate(idx):
                 n = int(cnt_h[i])
-                out.append((seg_h[i, :n].astype(np.int64) if n > 0 else np.array([]),
-                            feat_h[i, :n] if n > 0 else np.array([]), hidden_h[i]))
+                results[r] = (seg_h[i, :n].astype(np.int64) if n > 0 else np.array([]),
+                              feat_h[i, :n] if n > 0 else np.array([]), hidden_h[i])
+
+        pending = [None] * len(streams)                # per slot: the sub-batch whose buffers are still in use
+        for k, (idx, max_length) in enumerate(work):
+            slot = k % len(streams)
+            st = streams[slot]
+            if pending[slot] is not None:              # this slot's staging buffer, workspace and outputs are about to be reused
+                collect(pending[slot])
+                pending[slot] = None
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                chunk = [rows[i] for i in idx]
+                sub_len = [lengths[i] for i in idx]
+                if pcm:
+                    wav_dev, n_dev = eng.upload_pcm16(chunk, sub_len, max_length, slot)
+                else:
+                    wav_dev, n_dev = eng.upload(chunk, sub_len, max_length, slot)
+                hidden, seg, cnt, feat = eng.forward(wav_dev, n_dev, thr_n, thr_m, slot=slot)
+                hidden_h, hidden_pin = eng.pool.array(tuple(hidden.shape))
+                hidden_pin.copy_(hidden, non_blocking=True)
+                cnt_pin = torch.empty(cnt.shape, dtype=torch.int32, pin_memory=True)
+                cnt_pin.copy_(cnt, non_blocking=True)
+            pending[slot] = (st, idx, hidden_h, hidden_pin, seg, cnt_pin, feat)
+        # collect in launch order: the oldest sub-batch finishes first
+        n_w = len(work)
+        for k in range(max(0, n_w - len(streams)), n_w):
+            slot = k % len(streams)
+            if pending[slot] is not None:
+                collect(pending[slot])
+                pending[slot] = None
         main.wait_stream(streams[0])
-        return out
+        return results
 
     @torch.no_grad()
     def __call__(self, wav_file=None, wav=None, in_second=True, pcm16=None):
@@ -528,11 +552,7 @@ class Segmenter:
             buckets = plan_length_buckets(lengths, self.bucket_ratio, self.max_batch)
         else:
             buckets = [list(range(len(rows)))]
-        results = [None] * len(rows)
-        for idx in buckets:
-            sub_len = [lengths[i] for i in idx]
-            for i, r in zip(idx, self._run_rows([rows[i] for i in idx], sub_len, max(sub_len), pcm)):
-                results[i] = r
+        results = self._run_jobs(rows, lengths, [(idx, max(lengths[i] for i in idx)) for idx in buckets], pcm)
         outputs = [{'segments': seg * 1.0 / FRAME_RATE if in_second else seg,
                     'segment_features': feat, 'hidden_states': hid} for seg, feat, hid in results]
         return outputs if is_batch else outputs[0]
