@@ -104,14 +104,6 @@ bool make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t*
   return make_tmap(map, base, 2, rank, dims, strides_elems, 64, box1, 128, err);
 }
 
-// output maps over a channels-last [batches][rows][ld] tensor: fp32 box {32,32} swizzle 128B, fp16 box {32,32} swizzle 64B
-bool make_out_map(CUtensorMap* map, const void* base, int elem_bytes, int ld, int rows_per_batch, int batches,
-                  std::string* err) {
-  uint64_t dims[3] = {(uint64_t)ld, (uint64_t)rows_per_batch, (uint64_t)batches};
-  uint64_t str[3] = {1, (uint64_t)ld, (uint64_t)rows_per_batch * ld};
-  return make_tmap(map, base, elem_bytes, 3, dims, str, 32, 32, elem_bytes == 4 ? 128 : 64, err);
-}
-
 // ------------------------------------------------------------------------------------------------
 // small utility kernels (weight packing, dtype conversion)
 // ------------------------------------------------------------------------------------------------
@@ -260,8 +252,7 @@ struct LayerW {
 
 struct GemmOp {
   CUtensorMap a_hi, a_lo;
-  CUtensorMap o_f32, o_hi, o_lo;        // gemm_tc / gemm2_tc: {32, 32} boxes
-  CUtensorMap o3_f32, o3_hi, o3_lo;     // gemm3_tc: fp32 {16, 32} SWIZZLE_64B; fp16 {32, 32} SWIZZLE_64B (hi only) or {16, 32} plain
+  CUtensorMap o3_f32, o3_hi, o3_lo;     // fp32 {16, 32} SWIZZLE_64B; fp16 {32, 32} SWIZZLE_64B (hi only) or {16, 32} plain
   const PackedLinear* w = nullptr;
   GemmParams p;
 };
@@ -532,13 +523,7 @@ bool make_a_maps(syl_handle* h, GemmOp& op, const __half* hi, const __half* lo, 
 
 // output maps; any of the three destinations may be null
 bool make_o_maps(syl_handle* h, GemmOp& op, float* f32, __half* hi, __half* lo, int ld) {
-  memset(&op.o_f32, 0, sizeof(CUtensorMap));
-  memset(&op.o_hi, 0, sizeof(CUtensorMap));
-  memset(&op.o_lo, 0, sizeof(CUtensorMap));
   const int rows = op.p.rows_per_batch, nb = op.p.batches;
-  if (f32 && !make_out_map(&op.o_f32, f32, 4, ld, rows, nb, &h->err)) return false;
-  if (hi && !make_out_map(&op.o_hi, hi, 2, ld, rows, nb, &h->err)) return false;
-  if (lo && !make_out_map(&op.o_lo, lo, 2, ld, rows, nb, &h->err)) return false;
   memset(&op.o3_f32, 0, sizeof(CUtensorMap));
   memset(&op.o3_hi, 0, sizeof(CUtensorMap));
   memset(&op.o3_lo, 0, sizeof(CUtensorMap));
@@ -556,38 +541,6 @@ bool make_o_maps(syl_handle* h, GemmOp& op, float* f32, __half* hi, __half* lo, 
   return true;
 }
 
-int launch_gemm_raw(const GemmOp& op, const CUtensorMap& b_hi, const CUtensorMap& b_lo, cudaStream_t st, int sm_count) {
-  const GemmParams& p = op.p;
-  const int tiles_m = p.batches * ((p.rows_per_batch + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M);
-  const int tiles = tiles_m * (p.N / GEMM_BLOCK_N);
-  const int grid = std::min(tiles, sm_count);
-  if (grid <= 0) return SYL_OK;
-  gemm_tc_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_TOTAL, st>>>(op.a_hi, op.a_lo, b_hi, b_lo, op.o_f32, op.o_hi, op.o_lo, p);
-  return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
-}
-
-// 2-CTA clusters: 256-row tiles, each CTA of a pair owns 128 rows and half of the B tile
-int launch_gemm2_raw(const GemmOp& op, const CUtensorMap& b_hi, const CUtensorMap& b_lo, cudaStream_t st, int sm_count) {
-  const GemmParams& p = op.p;
-  const int tiles_m = p.batches * ((p.rows_per_batch + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M));
-  const int tiles = tiles_m * (p.N / GEMM_BLOCK_N);
-  const int clusters = std::min(tiles, sm_count / 2);
-  if (clusters <= 0) return SYL_OK;
-  launch_pdl(gemm2_tc_kernel, dim3(2 * clusters), dim3(GEMM_THREADS), GEMM2_SMEM_TOTAL, st, op.a_hi, op.a_lo, b_hi, b_lo, op.o_f32,
-             op.o_hi, op.o_lo, p);
-  return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
-}
-
-// 16-warp epilogue (gemm3_tc.cuh); SYL_GEMM_EPI16=0 falls back to the 8-warp gemm2 kernel for A/B timing
-bool gemm_use_epi16() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SYL_GEMM_EPI16");
-    v = e ? atoi(e) : 1;
-  }
-  return v != 0;
-}
-
 int launch_gemm3_raw(const GemmOp& op, const CUtensorMap& b_hi, const CUtensorMap& b_lo, cudaStream_t st, int sm_count) {
   const GemmParams& p = op.p;
   const int tiles_m = p.batches * ((p.rows_per_batch + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M));
@@ -599,23 +552,8 @@ int launch_gemm3_raw(const GemmOp& op, const CUtensorMap& b_hi, const CUtensorMa
   return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
 }
 
-bool gemm_use_2cta() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SYL_GEMM_2CTA");
-    v = e ? atoi(e) : 1;
-  }
-  return v != 0;
-}
-
 int launch_gemm(syl_handle* h, const GemmOp& op, cudaStream_t st, int sm_count) {
-  if (gemm_use_2cta()) {
-    const int rc = gemm_use_epi16() ? launch_gemm3_raw(op, op.w->map2_hi, op.w->map2_lo, st, sm_count)
-                                    : launch_gemm2_raw(op, op.w->map2_hi, op.w->map2_lo, st, sm_count);
-    if (rc != SYL_OK) return fail(h, SYL_E_CUDA, "gemm2/3 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-    return SYL_OK;
-  }
-  if (launch_gemm_raw(op, op.w->map_hi, op.w->map_lo, st, sm_count) != SYL_OK)
+  if (launch_gemm3_raw(op, op.w->map2_hi, op.w->map2_lo, st, sm_count) != SYL_OK)
     return fail(h, SYL_E_CUDA, "gemm launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   return SYL_OK;
 }
@@ -632,11 +570,8 @@ int launch_posconv(syl_handle* h, const PosOp& op, cudaStream_t st, int sm_count
 bool g_attrs_set = false;
 int ensure_attrs(syl_handle* h) {
   if (g_attrs_set) return SYL_OK;
-  CUDA_TRY(h, cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_TOTAL));
-  CUDA_TRY(h, cudaFuncSetAttribute(gemm2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL));
   CUDA_TRY(h, cudaFuncSetAttribute(gemm3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL));
   CUDA_TRY(h, cudaFuncSetAttribute(posconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM_TOTAL));
-  CUDA_TRY(h, cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
   CUDA_TRY(h, (cudaFuncSetAttribute(attention7_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL)));
   CUDA_TRY(h, (cudaFuncSetAttribute(attention7_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL)));
   CUDA_TRY(h, (cudaFuncSetAttribute(attention7_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL)));
@@ -819,24 +754,21 @@ int launch_attention(const CUtensorMap& qkv, const CUtensorMap& o_hi, const CUte
   ap.model_dim = kH;
   ap.kv_len = kv_len;
   ap.out_lo = out_lo;
-  // experiment switches (profiles/r02_attention.md): SYL_ATTN_IMPL=6 selects the lock-step kernel, SYL_ATTN_POLY the
-  // number of exp2 pairs (out of every four) computed on the FMA pipe, SYL_ATTN_DEBUG the arithmetic-removal probes
-  static int impl = -1, debug = 0, poly = 0;
-  if (impl < 0) {
+  // experiment switches (profiles/r02_attention.md): SYL_ATTN_POLY = exp2 pairs (out of every four) computed on the
+  // FMA pipe (0 or 1), SYL_ATTN_DEBUG = arithmetic-removal probes
+  static int init = 0, debug = 0, poly = 1;
+  if (!init) {
     const char* e = getenv("SYL_ATTN_DEBUG");
     debug = e ? atoi(e) : 0;
     e = getenv("SYL_ATTN_POLY");
     poly = e ? atoi(e) : 1;
-    e = getenv("SYL_ATTN_IMPL");
-    impl = e ? atoi(e) : 7;
+    init = 1;
   }
   ap.debug = debug;
   const int q_tiles = (T + ATT_BQ - 1) / ATT_BQ;
   const int items = B * kHeads * ((q_tiles + ATT_QT - 1) / ATT_QT);
   const int grid = std::min(items, sm_count);
-  if (impl == 6)
-    attention_kernel<<<grid, ATT_THREADS, ATT_SMEM_TOTAL, st>>>(qkv, o_hi, o_lo, ap);
-  else if (ap.trace)
+  if (ap.trace)
     launch_pdl(attention7_kernel<0, true>, dim3(grid), dim3(ATT7_THREADS), ATT7_SMEM_TOTAL, st, qkv, o_hi, o_lo, ap);
   else if (poly == 1)
     launch_pdl(attention7_kernel<1, false>, dim3(grid), dim3(ATT7_THREADS), ATT7_SMEM_TOTAL, st, qkv, o_hi, o_lo, ap);
@@ -858,15 +790,7 @@ int run_frontend(syl_handle* h, const float* wav, cudaStream_t st) {
                at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift));
     __half* hi = at<__half>(ws, L.act_hi[0]);
     __half* lo = conv_split(h->mode, 1) ? at<__half>(ws, L.act_lo[0]) : nullptr;
-    static int conv0_impl = -1;        // SYL_CONV0_IMPL=0: the FFMA kernel (kept for A/B timing), default: mma.sync
-    if (conv0_impl < 0) {
-      const char* e = getenv("SYL_CONV0_IMPL");
-      conv0_impl = e ? atoi(e) : 1;
-    }
-    if (conv0_impl == 0)
-      conv0_apply_kernel<<<dim3((L0 + C0A_T - 1) / C0A_T, B), C0A_THREADS, 0, st>>>(
-          wav, pl.t_samp, L0, h->conv0_w, at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift), hi, lo);
-    else if (lo)
+    if (lo)
       launch_pdl(conv0_mma_kernel<true>, dim3((L0 + C0M_T - 1) / C0M_T, B), dim3(C0M_THREADS), 0, st, wav, pl.t_samp, L0,
                  h->conv0_bfrag, at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift), hi, lo);
     else
@@ -1107,7 +1031,7 @@ int syl_set_active_layers(syl_handle* h, int n) {
 int syl_forward_launch_count(const syl_handle* h, int with_segmentation) {
   if (!h) return 0;
   const int nl = (h->active_layers >= 0 && h->active_layers < h->n_layers) ? h->active_layers : h->n_layers;
-  // valid_frames, moments, gn_coeff, conv0_apply, 6 conv GEMMs, LN512, proj, pos, LN ; per layer 4 GEMM + attn + 2 LN
+  // valid_frames, moments, gn_coeff, conv0_mma, 6 conv GEMMs, LN512, proj, pos, LN ; per layer 4 GEMM + attn + 2 LN
   return 4 + 6 + 4 + nl * 7 + (with_segmentation ? 3 : 0);
 }
 
@@ -1279,8 +1203,7 @@ int syl_encoder_layer(syl_handle* h, int layer, const float* h_in, const int32_t
 int syl_attention(const void* qkv_f16, const int32_t* kv_len, int batch, int T, void* out_f16, void* stream) {
   std::string err;
   if (!qkv_f16 || !out_f16 || batch <= 0 || T <= 0) return fail(nullptr, SYL_E_ARG, "syl_attention: bad arguments");
-  if (cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL) != cudaSuccess ||
-      cudaFuncSetAttribute(attention7_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL) != cudaSuccess ||
+  if (cudaFuncSetAttribute(attention7_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL) != cudaSuccess ||
       cudaFuncSetAttribute(attention7_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL) != cudaSuccess ||
       cudaFuncSetAttribute(attention7_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL) != cudaSuccess)
     return fail(nullptr, SYL_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1366,8 +1289,6 @@ int syl_gemm_f32(const float* A, const float* W, const float* bias, const float*
   if (N % 256 != 0 || K % 64 != 0) return fail(nullptr, SYL_E_ARG, "syl_gemm_f32: N must be a multiple of 256 and K of 64");
   if (n_pass != 1 && n_pass != 3) return fail(nullptr, SYL_E_ARG, "syl_gemm_f32: n_pass must be 1 or 3");
   if (workspace_bytes < syl_gemm_workspace_bytes(M, N, K)) return fail(nullptr, SYL_E_WORKSPACE, "syl_gemm_f32: workspace too small");
-  if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_TOTAL) != cudaSuccess)
-    return fail(nullptr, SYL_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   auto al = [](size_t b) { return (b + 1023) & ~size_t(1023); };
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
@@ -1378,18 +1299,12 @@ int syl_gemm_f32(const float* A, const float* W, const float* bias, const float*
   split_f32_kernel<<<grid_for((size_t)M * K), 256, 0, st>>>(A, a_hi, a_lo, (size_t)M * K);
   split_f32_kernel<<<grid_for((size_t)N * K), 256, 0, st>>>(W, w_hi, w_lo, (size_t)N * K);
   std::string err;
-  CUtensorMap b_hi, b_lo;
   uint64_t wd[2] = {(uint64_t)K, (uint64_t)N}, wsd[2] = {1, (uint64_t)K};
-  if (!make_tmap_f16(&b_hi, w_hi, 2, wd, wsd, 256, &err) || !make_tmap_f16(&b_lo, w_lo, 2, wd, wsd, 256, &err))
-    return fail(nullptr, SYL_E_CUDA, "%s", err.c_str());
   GemmOp op;
   op.p = base_params();
   uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, 1}, str[3] = {1, (uint64_t)K, (uint64_t)M * K};
   if (!make_tmap_f16(&op.a_hi, a_hi, 3, dims, str, 128, &err) || !make_tmap_f16(&op.a_lo, a_lo, 3, dims, str, 128, &err))
     return fail(nullptr, SYL_E_CUDA, "%s", err.c_str());
-  memset(&op.o_hi, 0, sizeof(CUtensorMap));
-  memset(&op.o_lo, 0, sizeof(CUtensorMap));
-  if (!make_out_map(&op.o_f32, out, 4, N, M, 1, &err)) return fail(nullptr, SYL_E_CUDA, "%s", err.c_str());
   memset(&op.o3_hi, 0, sizeof(CUtensorMap));
   memset(&op.o3_lo, 0, sizeof(CUtensorMap));
   {
@@ -1407,19 +1322,13 @@ int syl_gemm_f32(const float* A, const float* W, const float* bias, const float*
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (gemm_use_2cta()) {
-    if (cudaFuncSetAttribute(gemm2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL) != cudaSuccess)
-      return fail(nullptr, SYL_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
-    CUtensorMap b2_hi, b2_lo;
-    if (!make_tmap_f16(&b2_hi, w_hi, 2, wd, wsd, 128, &err) || !make_tmap_f16(&b2_lo, w_lo, 2, wd, wsd, 128, &err))
-      return fail(nullptr, SYL_E_CUDA, "%s", err.c_str());
-    if (cudaFuncSetAttribute(gemm3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL) != cudaSuccess)
-      return fail(nullptr, SYL_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
-    if ((gemm_use_epi16() ? launch_gemm3_raw(op, b2_hi, b2_lo, st, sms) : launch_gemm2_raw(op, b2_hi, b2_lo, st, sms)) != SYL_OK)
-      return fail(nullptr, SYL_E_CUDA, "gemm2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-  } else if (launch_gemm_raw(op, b_hi, b_lo, st, sms) != SYL_OK) {
-    return fail(nullptr, SYL_E_CUDA, "gemm launch failed");
-  }
+  CUtensorMap b2_hi, b2_lo;     // this CTA's half of the B tile
+  if (!make_tmap_f16(&b2_hi, w_hi, 2, wd, wsd, 128, &err) || !make_tmap_f16(&b2_lo, w_lo, 2, wd, wsd, 128, &err))
+    return fail(nullptr, SYL_E_CUDA, "%s", err.c_str());
+  if (cudaFuncSetAttribute(gemm3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL) != cudaSuccess)
+    return fail(nullptr, SYL_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (launch_gemm3_raw(op, b2_hi, b2_lo, st, sms) != SYL_OK)
+    return fail(nullptr, SYL_E_CUDA, "gemm launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (residual) add_inplace_kernel<<<grid_for((size_t)M * N), 256, 0, st>>>(out, residual, (size_t)M * N);
   return cudaGetLastError() == cudaSuccess ? SYL_OK : fail(nullptr, SYL_E_CUDA, "launch failed");
 }

@@ -111,68 +111,9 @@ __global__ void conv0_gn_coeff_kernel(const double* __restrict__ part, int chunk
 }
 
 // ----------------------------------------------------------------------------------------------
-// conv0 + GroupNorm + GELU, written channels-last as fp16 hi (+ lo):  out[b, t, c]
-// grid (ceil(L0/64), B), block 128; each thread owns 4 consecutive channels.  The stage is bound by instruction
-// issue rather than HBM (about 10 FMA + 1 GroupNorm FMA + a GELU per output element), so the GELU runs on channel
-// pairs as packed fp32 (gelu_fast2).  Packing the 10-tap dot products as well (frames t, t+1 as a pair) was tried
-// and measured slower (0.88 vs 0.73 ms): the extra shared-memory reads and pair moves outweigh the FFMA2 savings.
-// ----------------------------------------------------------------------------------------------
-constexpr int C0A_THREADS = 128;
-constexpr int C0A_T = 64;
-
-__global__ void __launch_bounds__(C0A_THREADS)
-conv0_apply_kernel(const float* __restrict__ wav, int t_samp, int L0, const float* __restrict__ w0,
-                   const float* __restrict__ scale, const float* __restrict__ shift, __half* __restrict__ out_hi,
-                   __half* __restrict__ out_lo) {
-  __shared__ float xs[C0A_T * C0_S + C0_K];
-  const int b = blockIdx.y;
-  const int t0 = blockIdx.x * C0A_T;
-  const int nt = min(C0A_T, L0 - t0);
-  const float* w = wav + (size_t)b * t_samp + (size_t)t0 * C0_S;
-  const int nsamp = nt * C0_S + (C0_K - C0_S);
-  for (int i = threadIdx.x; i < nsamp; i += C0A_THREADS) xs[i] = w[i];
-
-  const int c0 = threadIdx.x * 4;
-  float wr[4][C0_K], sc[4], sh[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-#pragma unroll
-    for (int j = 0; j < C0_K; ++j) wr[q][j] = w0[(c0 + q) * C0_K + j];
-    sc[q] = scale[b * C0_OUT + c0 + q];
-    sh[q] = shift[b * C0_OUT + c0 + q];
-  }
-  __syncthreads();
-
-  for (int t = 0; t < nt; ++t) {
-    float x[C0_K];
-#pragma unroll
-    for (int j = 0; j < C0_K; ++j) x[j] = xs[t * C0_S + j];
-    float g[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float y = 0.0f;
-#pragma unroll
-      for (int j = 0; j < C0_K; ++j) y = fmaf(wr[q][j], x[j], y);
-      g[q] = fmaf(y, sc[q], sh[q]);
-    }
-    gelu_fast2(g[0], g[1], g[0], g[1]);
-    gelu_fast2(g[2], g[3], g[2], g[3]);
-    const size_t o = ((size_t)b * L0 + t0 + t) * C0_OUT + c0;
-    if (out_lo) {
-      uint32_t h0, l0, h1, l1;
-      split_pair(g[0], g[1], h0, l0);
-      split_pair(g[2], g[3], h1, l1);
-      *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(h0, h1);
-      *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(l0, l1);
-    } else {
-      *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(pack_f16x2_sat(g[0], g[1]), pack_f16x2_sat(g[2], g[3]));
-    }
-  }
-}
-
-// ----------------------------------------------------------------------------------------------
 // conv0 + GroupNorm + GELU with the 10-tap dot products on the tensor cores (warp-level mma.sync m16n8k16).
-// conv0_apply_kernel above is bound by instruction issue: 10 FFMA + ~13 other instructions per output element.
+// The round-1 kernel (10 FFMA + ~13 other instructions per output element, one thread per 4 channels) was bound by
+// instruction issue: 0.66 ms against 0.43 ms here (profiles/r02_bench_ab.md).  Output channels-last fp16 hi (+ lo).
 // Here a warp computes [16 frames] x [8 channels] x [K = 16: taps 0-9, zero padded] per MMA; the fp32 waveform and
 // weights enter as fp16 hi + lo and three MMAs (hi*hi, lo*hi, hi*lo) accumulate in fp32, which keeps 22 significant
 // bits of both operands (the GEMM kernels' split scheme).  What remains per element is the GroupNorm FFMA2, the GELU

@@ -1,5 +1,11 @@
-// gemm2_tc_kernel with SIXTEEN epilogue warps (640 threads): same producer, MMA issuer, tiles and shared-memory
-// budget, but four epilogue warps per scheduler instead of two.  With K = 768 (12 k-blocks, ~6 100 tensor cycles per
+// Persistent, warp-specialised tcgen05 GEMM on 2-CTA clusters (plumbing: gemm2_tc.cuh) with SIXTEEN epilogue warps
+// (640 threads): four epilogue warps per scheduler instead of the two of its round-1 predecessor.
+//   warp 0      : TMA producer (one elected lane) - A/B tiles, 128B-swizzled, K-major, 6-stage mbarrier ring
+//   warp 1      : MMA issuer (leader CTA, one elected lane) - tcgen05.mma.cta_group::2 kind::f16, fp32 accumulators
+//                 in TMEM, two accumulator stages so the epilogue overlaps the next tile
+//   warp 2      : TMEM allocator / deallocator
+//   warps 4..19 : epilogue - tcgen05.ld (software pipelined), bias / scale / GELU / row mask in registers, staging in
+//                 shared memory, TMA stores (fp32 and/or fp16 hi(+lo)); no thread ever issues a global store  With K = 768 (12 k-blocks, ~6 100 tensor cycles per
 // tile) the 8-warp epilogue - two warps per scheduler walking 128 columns each through dependent MUFU / convert /
 // store chains - took longer than the main loop: QKV ran at 77 %, FFN1 (GELU) at 61-72 % and the out-projection at
 // 50 % tensor-pipe activity (profiles/r02_ncu_summary.md).  Each warp now owns a [32 rows x 64 columns] block and
@@ -15,7 +21,7 @@ namespace syl {
 constexpr int GEMM3_EPI_WARPS = 16;
 constexpr int GEMM3_THREADS = (GEMM_EPI_WARP0 + GEMM3_EPI_WARPS) * 32;   // 640
 constexpr int GEMM3_EPI_STAGE_BYTES = 2048;
-static_assert(GEMM3_EPI_WARPS * GEMM3_EPI_STAGE_BYTES == GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES, "same staging area as gemm2");
+static_assert(GEMM3_EPI_WARPS * GEMM3_EPI_STAGE_BYTES == GEMM2_EPI_BYTES, "staging area");
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM3_THREADS, 1)
 gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__ CUtensorMap a_lo,
@@ -28,7 +34,7 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // SWIZZLE_128B tiles need 1024-byte aligned stage buffers
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + GEMM2_STAGES * GEMM2_A_BYTES;
-  uint8_t* smem_epi = smem + GEMM2_SMEM_EPI;   // same 32 KB as gemm2: 16 warps x 2 KB
+  uint8_t* smem_epi = smem + GEMM2_SMEM_EPI;   // 16 warps x 2 KB
   float* smem_bias = reinterpret_cast<float*>(smem + GEMM2_SMEM_BIAS);   // [2][256]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM2_SMEM_BAR);
   uint64_t* full_bar = bars;                           // [STAGES]  (used in the leader CTA)

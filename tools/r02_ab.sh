@@ -1,5 +1,7 @@
 #!/bin/bash
-# Round-2 A/B matrix on one B200: every new kernel against the one it replaces, through bench.py's stage timers.
+# Round-2 A/B matrix on one B200: every new kernel against the one it replaced, through bench.py's stage timers.
+# HISTORICAL: the SYL_GEMM_EPI / SYL_CONV0_IMPL / SYL_ATTN_IMPL switches selected kernels that were removed after this
+# script produced profiles/r02_bench_ab.md (commit "Remove superseded kernels"); check that commit out to re-run it.
 # Usage (under gpurun): bash tools/r02_ab.sh   -> logs in gpurun_out/r02_ab/
 set -u
 out=gpurun_out/r02_ab
