@@ -108,6 +108,15 @@ int syl_attention_trace(const void* qkv_f16, const int32_t* kv_len, int batch, i
 size_t syl_pcm16_workspace_bytes(int batch, int t_samp_max);
 int syl_prepare_pcm16(const int16_t* pcm, const int64_t* offsets, const int32_t* n_samples, int batch, int t_samp_max,
                       int normalize, float* wav_out, void* workspace, size_t workspace_bytes, void* stream);
+/* the same for fp32 samples (e.g. the output of syl_resample) */
+int syl_prepare_f32(const float* wav, const int64_t* offsets, const int32_t* n_samples, int batch, int t_samp_max,
+                    int normalize, float* wav_out, void* workspace, size_t workspace_bytes, void* stream);
+/* Band-limited sinc resampling, replaces torchaudio.transforms.Resample(sr, 16000) (sylber/model/sylber.py:85):
+ * wav_in [batch, t_in_max] fp32 with n_in[b] valid samples, kernel [new_g, 2 * width + orig_g] from
+ * sylber_b200/resample.py (frequencies reduced by their gcd); wav_out [batch, t_out_max], zero filled beyond
+ * n_out[b] = ceil(new_g * n_in[b] / orig_g) (n_out may be null). */
+int syl_resample(const float* wav_in, const int32_t* n_in, int batch, int t_in_max, const float* kernel, int orig_g, int new_g,
+                 int width, float* wav_out, int32_t* n_out, int t_out_max, void* stream);
 /* Back door, replaces the codebook search of KMQuantizer.get_indices (sylber/model/quantizer.py:86-110):
  * idx_out[r] = argmin_k |x_r - c_k|^2 over centroids [K, 768] (first minimum wins); normalize != 0 applies
  * x / sqrt(sum x^2 + 1e-8) * 6 first (quantizer.py:99); dist_out (optional) receives the squared distances. */

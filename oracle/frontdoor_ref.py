@@ -15,11 +15,15 @@ import torch
 from . import segment_ref
 
 
-def normalize_pcm16(pcm_list, normalize=True):
-    """list of 1-D int16 arrays -> (B, T_max) fp32 tensor, zero padded, and the lengths."""
+def normalize_pcm16(pcm_list, normalize=True, sample_rate=16000):
+    """list of 1-D int16 arrays -> (B, T_max) fp32 tensor, zero padded, and the lengths.  sample_rate != 16000 applies
+    the reference's own resampler between the conversion and the normalisation (sylber.py:84-86)."""
     rows = []
     for x in pcm_list:
         w = torch.from_numpy(np.asarray(x, dtype=np.int16).astype(np.float32) / 32768.0)[None, :]
+        if sample_rate != 16000:
+            import torchaudio
+            w = torchaudio.transforms.Resample(sample_rate, 16000)(w)
         if normalize:
             w = (w - w.mean()) / w.std()
         rows.append(w[0])

@@ -40,6 +40,9 @@ SIGNATURES = {
     "syl_attention_trace": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_int, _c_void_p]),
     "syl_pcm16_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
     "syl_prepare_pcm16": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
+    "syl_prepare_f32": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
+    "syl_resample": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_int,
+                              _c_void_p]),
     "syl_kmeans_assign": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p]),
     "syl_segment_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
     "syl_segment": (_c_int, [_c_void_p, _c_int, _c_int, _c_float, _c_float, _c_void_p, _c_void_p, _c_void_p, _c_int,

@@ -1247,9 +1247,32 @@ int syl_prepare_pcm16(const int16_t* pcm, const int64_t* offsets, const int32_t*
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int chunks = (t_samp_max + PCM_CHUNK - 1) / PCM_CHUNK;
   double* part = reinterpret_cast<double*>(workspace);
-  if (normalize) pcm16_stats_kernel<<<dim3(chunks, batch), PCM_THREADS, 0, st>>>(pcm, offsets, n_samples, chunks, part);
-  pcm16_apply_kernel<<<dim3(chunks, batch), PCM_THREADS, 0, st>>>(pcm, offsets, n_samples, chunks, part, normalize, t_samp_max, wav_out);
+  if (normalize) pcm16_stats_kernel<int16_t><<<dim3(chunks, batch), PCM_THREADS, 0, st>>>(pcm, offsets, n_samples, chunks, part);
+  pcm16_apply_kernel<int16_t><<<dim3(chunks, batch), PCM_THREADS, 0, st>>>(pcm, offsets, n_samples, chunks, part, normalize, t_samp_max, wav_out);
   return cudaGetLastError() == cudaSuccess ? SYL_OK : fail(nullptr, SYL_E_CUDA, "syl_prepare_pcm16 launch failed");
+}
+
+int syl_prepare_f32(const float* wav, const int64_t* offsets, const int32_t* n_samples, int batch, int t_samp_max,
+                    int normalize, float* wav_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!wav || !offsets || !n_samples || !wav_out || !workspace || batch <= 0 || t_samp_max <= 0)
+    return fail(nullptr, SYL_E_ARG, "syl_prepare_f32: bad arguments");
+  if (workspace_bytes < syl_pcm16_workspace_bytes(batch, t_samp_max))
+    return fail(nullptr, SYL_E_WORKSPACE, "syl_prepare_f32: workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int chunks = (t_samp_max + PCM_CHUNK - 1) / PCM_CHUNK;
+  double* part = reinterpret_cast<double*>(workspace);
+  if (normalize) pcm16_stats_kernel<float><<<dim3(chunks, batch), PCM_THREADS, 0, st>>>(wav, offsets, n_samples, chunks, part);
+  pcm16_apply_kernel<float><<<dim3(chunks, batch), PCM_THREADS, 0, st>>>(wav, offsets, n_samples, chunks, part, normalize, t_samp_max, wav_out);
+  return cudaGetLastError() == cudaSuccess ? SYL_OK : fail(nullptr, SYL_E_CUDA, "syl_prepare_f32 launch failed");
+}
+
+int syl_resample(const float* wav_in, const int32_t* n_in, int batch, int t_in_max, const float* kernel, int orig_g, int new_g,
+                 int width, float* wav_out, int32_t* n_out, int t_out_max, void* stream) {
+  if (!wav_in || !n_in || !kernel || !wav_out || batch <= 0 || t_in_max <= 0 || t_out_max <= 0 || orig_g <= 0 || new_g <= 0 || width < 0)
+    return fail(nullptr, SYL_E_ARG, "syl_resample: bad arguments");
+  resample_kernel<<<dim3((t_out_max + 255) / 256, batch), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      wav_in, n_in, t_in_max, kernel, orig_g, new_g, width, wav_out, n_out, t_out_max);
+  return cudaGetLastError() == cudaSuccess ? SYL_OK : fail(nullptr, SYL_E_CUDA, "syl_resample launch failed");
 }
 
 int syl_kmeans_assign(const float* feats, int n, const float* centroids, int K, int normalize, int32_t* idx_out,

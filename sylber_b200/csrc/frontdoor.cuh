@@ -14,10 +14,14 @@ namespace syl {
 constexpr int PCM_THREADS = 256;
 constexpr int PCM_CHUNK = 8192;          // samples per block
 
-// partial (sum, sum of squares) of x / 32768 per (utterance, chunk), fp64 so that the statistics do not depend on
-// the summation order beyond rounding of the final result
+__device__ __forceinline__ float pcm_to_float(int16_t v) { return (float)v * (1.0f / 32768.0f); }
+__device__ __forceinline__ float pcm_to_float(float v) { return v; }
+
+// partial (sum, sum of squares) of the samples (int16 / 32768, or fp32 as is) per (utterance, chunk), fp64 so that the
+// statistics do not depend on the summation order beyond rounding of the final result
+template <typename TIn>
 __global__ void __launch_bounds__(PCM_THREADS)
-pcm16_stats_kernel(const int16_t* __restrict__ pcm, const int64_t* __restrict__ offsets, const int32_t* __restrict__ n_samples,
+pcm16_stats_kernel(const TIn* __restrict__ pcm, const int64_t* __restrict__ offsets, const int32_t* __restrict__ n_samples,
                    int chunks, double* __restrict__ part) {
   __shared__ double red[2][PCM_THREADS / 32];
   const int b = blockIdx.y;
@@ -26,7 +30,7 @@ pcm16_stats_kernel(const int16_t* __restrict__ pcm, const int64_t* __restrict__ 
   const int i0 = blockIdx.x * PCM_CHUNK;
   double s = 0.0, q = 0.0;
   for (int i = i0 + threadIdx.x; i < min(i0 + PCM_CHUNK, n); i += PCM_THREADS) {
-    const double x = (double)pcm[base + i] * (1.0 / 32768.0);
+    const double x = (double)pcm_to_float(pcm[base + i]);
     s += x;
     q += x * x;
   }
@@ -51,9 +55,10 @@ pcm16_stats_kernel(const int16_t* __restrict__ pcm, const int64_t* __restrict__ 
   }
 }
 
-// out[b, i] = (x_i / 32768 - mean) / std for i < n (normalize) or x_i / 32768 (plain), 0 for n <= i < t_max
+// out[b, i] = (x_i - mean) / std for i < n (normalize) or x_i (plain), 0 for n <= i < t_max
+template <typename TIn>
 __global__ void __launch_bounds__(PCM_THREADS)
-pcm16_apply_kernel(const int16_t* __restrict__ pcm, const int64_t* __restrict__ offsets, const int32_t* __restrict__ n_samples,
+pcm16_apply_kernel(const TIn* __restrict__ pcm, const int64_t* __restrict__ offsets, const int32_t* __restrict__ n_samples,
                    int chunks, const double* __restrict__ part, int normalize, int t_max, float* __restrict__ out) {
   __shared__ float s_mean, s_rstd;
   const int b = blockIdx.y;
@@ -81,9 +86,37 @@ pcm16_apply_kernel(const int16_t* __restrict__ pcm, const int64_t* __restrict__ 
   const int i0 = blockIdx.x * PCM_CHUNK;
   for (int i = i0 + threadIdx.x; i < min(i0 + PCM_CHUNK, t_max); i += PCM_THREADS) {
     float v = 0.0f;
-    if (i < n) v = ((float)pcm[base + i] * (1.0f / 32768.0f) - mean) * rstd;
+    if (i < n) v = (pcm_to_float(pcm[base + i]) - mean) * rstd;
     out[(size_t)b * t_max + i] = v;
   }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Band-limited sinc resampling (torchaudio.transforms.Resample, sylber.py:85): one windowed-sinc FIR per output phase,
+//   out[b, i * new_g + p] = sum_k h[p, k] * xpad[i * orig_g + k],   xpad = x with `width` zeros in front and zeros behind,
+// h [new_g, K = 2 width + orig_g] from sylber_b200/resample.py.  n_out[b] = ceil(new_g * n_in[b] / orig_g); the rest of
+// the row is zero filled.  grid (ceil(t_out_max / 256), B), block 256: one output sample per thread.
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+resample_kernel(const float* __restrict__ in, const int32_t* __restrict__ n_in, int t_in_max, const float* __restrict__ h,
+                int orig_g, int new_g, int width, float* __restrict__ out, int32_t* __restrict__ n_out, int t_out_max) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = n_in[b];
+  const int nout = (int)(((long long)new_g * n + orig_g - 1) / orig_g);
+  if (j == 0 && n_out) n_out[b] = nout;
+  if (j >= t_out_max) return;
+  float acc = 0.0f;
+  if (j < nout) {
+    const int i = j / new_g, p = j - i * new_g;
+    const int K = 2 * width + orig_g;
+    const float* hp = h + (size_t)p * K;
+    const float* x = in + (size_t)b * t_in_max;
+    const int m0 = i * orig_g - width;                  // sample index of tap 0
+    const int k_lo = max(0, -m0), k_hi = min(K, n - m0);
+    for (int k = k_lo; k < k_hi; ++k) acc = fmaf(__ldg(hp + k), x[m0 + k], acc);
+  }
+  out[(size_t)b * t_out_max + j] = acc;
 }
 
 // ----------------------------------------------------------------------------------------------------------------

@@ -8,6 +8,7 @@ encoder, the segmentation scan and the pooling on the GPU and hands back NumPy a
 from __future__ import annotations
 
 import ctypes
+import math
 import os
 import weakref
 from pathlib import Path
@@ -18,6 +19,7 @@ import torch
 
 from . import _lib
 from .batching import plan_length_buckets
+from .resample import sinc_resample_kernel, resampled_length
 from .weights import normalize_state_dict, random_hubert_state_dict, REQUIRED_KEYS
 
 HIDDEN = 768
@@ -81,6 +83,7 @@ class _Engine:
         self._io = {}
         self._stage_in = {}
         self._streams = []
+        self._resamplers = {}
         self.pool = _PinnedPool()
         missing = [k for k in REQUIRED_KEYS(n_layers) if k not in state_dict]
         if missing:
@@ -164,11 +167,21 @@ class _Engine:
         n_dev.copy_(n_host, non_blocking=True)
         return wav_dev, n_dev
 
-    def upload_pcm16(self, rows, lengths, max_length, slot):
-        """int16 PCM rows -> the slot's (B, max_length) fp32 device batch, converted, z-normalised and zero padded on
-        the GPU (syl_prepare_pcm16, sylber.py:83-87 + :93-118).  The samples travel back to back as int16."""
+    def _resampler(self, sample_rate):
+        """Device copy of the sinc filter bank for sample_rate -> 16 kHz (cached per rate)."""
+        ent = self._resamplers.get(sample_rate)
+        if ent is None:
+            k, width, orig_g, new_g = sinc_resample_kernel(sample_rate, 16000)
+            ent = self._resamplers[sample_rate] = (torch.from_numpy(k).to(self.device).contiguous(), width, orig_g, new_g)
+        return ent
+
+    def upload_pcm16(self, rows, lengths, max_length, slot, sample_rate=16000):
+        """int16 PCM rows -> the slot's (B, max_length) fp32 device batch, converted, (resampled,) z-normalised and
+        zero padded on the GPU (syl_prepare_pcm16 / syl_resample / syl_prepare_f32; sylber.py:83-87 + :93-118).
+        The samples travel back to back as int16.  `lengths` / `max_length` count 16 kHz samples."""
         B = len(rows)
-        total = sum(lengths)
+        in_len = [int(r.shape[-1]) for r in rows]
+        total = sum(in_len)
         key = ("pcm", slot)
         buf = self._stage_in.get(key)
         if buf is None or buf[0].numel() < total or buf[2].numel() < B:
@@ -178,7 +191,7 @@ class _Engine:
                                          torch.empty(max(B, 64), dtype=torch.int64, device=self.device))
         host, dev, off_dev = buf
         offsets, o = [], 0
-        for r, n in zip(rows, lengths):
+        for r, n in zip(rows, in_len):
             host[o:o + n].copy_(r)
             offsets.append(o)
             o += n
@@ -186,14 +199,29 @@ class _Engine:
         off_dev[:B].copy_(torch.tensor(offsets, dtype=torch.int64), non_blocking=True)
         wav_dev, n_dev = self.device_input(slot, B, max_length)
         n_dev.copy_(torch.tensor(lengths, dtype=torch.int32), non_blocking=True)
-        need = int(self.lib.syl_pcm16_workspace_bytes(B, max_length))
+        t_in = max(in_len)
+        need = int(self.lib.syl_pcm16_workspace_bytes(B, max(max_length, t_in)))
         ws = self._stage_in.get(("pcm_ws", slot))
         if ws is None or ws.numel() < need:
             ws = self._stage_in[("pcm_ws", slot)] = torch.empty(need, dtype=torch.uint8, device=self.device)
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        rc = self.lib.syl_prepare_pcm16(_ptr(dev), _ptr(off_dev), _ptr(n_dev), B, max_length, 1, _ptr(wav_dev), _ptr(ws), need,
-                                        ctypes.c_void_p(stream))
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        if sample_rate == 16000:
+            rc = self.lib.syl_prepare_pcm16(_ptr(dev), _ptr(off_dev), _ptr(n_dev), B, max_length, 1, _ptr(wav_dev), _ptr(ws), need,
+                                            stream)
+            _lib.check(self.lib, None, rc, "syl_prepare_pcm16")
+            return wav_dev, n_dev
+        # other rates (sylber.py:84-86): int16 -> fp32, sinc resampling to 16 kHz, then (w - mean) / std - all on the device
+        kern, width, orig_g, new_g = self._resampler(sample_rate)
+        n_in = torch.tensor(in_len, dtype=torch.int32).to(self.device, non_blocking=True)
+        raw = torch.empty((B, t_in), dtype=torch.float32, device=self.device)
+        rc = self.lib.syl_prepare_pcm16(_ptr(dev), _ptr(off_dev), _ptr(n_in), B, t_in, 0, _ptr(raw), _ptr(ws), need, stream)
         _lib.check(self.lib, None, rc, "syl_prepare_pcm16")
+        res = torch.empty((B, max_length), dtype=torch.float32, device=self.device)
+        rc = self.lib.syl_resample(_ptr(raw), _ptr(n_in), B, t_in, _ptr(kern), orig_g, new_g, width, _ptr(res), None, max_length, stream)
+        _lib.check(self.lib, None, rc, "syl_resample")
+        row_off = (torch.arange(B, dtype=torch.int64) * max_length).to(self.device, non_blocking=True)
+        rc = self.lib.syl_prepare_f32(_ptr(res), _ptr(row_off), _ptr(n_dev), B, max_length, 1, _ptr(wav_dev), _ptr(ws), need, stream)
+        _lib.check(self.lib, None, rc, "syl_prepare_f32")
         return wav_dev, n_dev
 
     def segment_states(self, states, thr_norm, thr_merge):
@@ -458,8 +486,8 @@ class Segmenter:
                 a += k
         return bounds
 
-    def _run_jobs(self, rows, lengths, jobs, pcm=False):
-        """Padded batches through the engine.  rows: 1-D fp32 CPU tensors (or int16 when `pcm`); jobs: list of
+    def _run_jobs(self, rows, lengths, jobs, pcm=0):
+        """Padded batches through the engine.  rows: 1-D fp32 CPU tensors (or int16 at `pcm` Hz when pcm != 0); jobs: list of
         (row indices, max_length) - every row of a job is padded to that job's max_length (results depend on it, 8a).
         Returns per row (segments int64 (N,2) | empty, segment_features (N,768) | empty, hidden).
 
@@ -504,7 +532,7 @@ class Segmenter:
                 chunk = [rows[i] for i in idx]
                 sub_len = [lengths[i] for i in idx]
                 if pcm:
-                    wav_dev, n_dev = eng.upload_pcm16(chunk, sub_len, max_length, slot)
+                    wav_dev, n_dev = eng.upload_pcm16(chunk, sub_len, max_length, slot, pcm)
                 else:
                     wav_dev, n_dev = eng.upload(chunk, sub_len, max_length, slot)
                 hidden, seg, cnt, feat = eng.forward(wav_dev, n_dev, thr_n, thr_m, slot=slot)
@@ -524,14 +552,15 @@ class Segmenter:
         return results
 
     @torch.no_grad()
-    def __call__(self, wav_file=None, wav=None, in_second=True, pcm16=None):
+    def __call__(self, wav_file=None, wav=None, in_second=True, pcm16=None, sample_rate=16000):
         """Same contract as the reference: a dict (single input) or list of dicts with
         `segments` (N,2), `segment_features` (N,768) float32, `hidden_states` (T_max,768) float32.
 
-        `pcm16=` (extension): one or a list of 1-D int16 arrays / tensors of 16 kHz mono PCM.  Equivalent to the
-        reference's file branch (x / 32768, then (w - mean) / std, sylber.py:83-87) with the conversion,
-        normalisation and padding done on the GPU (syl_prepare_pcm16) - half the host->device bytes."""
-        pcm = pcm16 is not None
+        `pcm16=` (extension): one or a list of 1-D int16 arrays / tensors of mono PCM at `sample_rate` Hz.  Equivalent
+        to the reference's file branch (x / 32768, resampling to 16 kHz if needed, then (w - mean) / std,
+        sylber.py:83-87) with conversion, resampling, normalisation and padding done on the GPU (syl_prepare_pcm16,
+        syl_resample, syl_prepare_f32) - half the host->device bytes."""
+        pcm = int(sample_rate) if pcm16 is not None else 0
         if pcm:
             is_batch = isinstance(pcm16, (list, tuple))
             rows = [torch.as_tensor(np.ascontiguousarray(x) if isinstance(x, np.ndarray) else x).reshape(-1)
@@ -547,6 +576,9 @@ class Segmenter:
                     w = w[None, :]
                 rows.extend(w[i] for i in range(w.shape[0]))      # torch.cat(dim=0) at sylber.py:117: channels become rows
         lengths = [int(r.shape[-1]) for r in rows]
+        if pcm and pcm != 16000:                       # lengths count 16 kHz samples from here on
+            g = math.gcd(pcm, 16000)
+            lengths = [resampled_length(n, pcm // g, 16000 // g) for n in lengths]
         if self.bucket_ratio:
             # opt-in deviation from the reference's padding semantics (batching.py): each bucket is padded to its own max
             buckets = plan_length_buckets(lengths, self.bucket_ratio, self.max_batch)

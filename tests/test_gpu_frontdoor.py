@@ -138,3 +138,43 @@ def test_bucketed_batching_equals_per_bucket_calls(seg9):
             assert got[i]["hidden_states"].shape == w["hidden_states"].shape        # padded to the BUCKET's maximum
             assert np.array_equal(got[i]["hidden_states"], w["hidden_states"])
             assert np.array_equal(np.asarray(got[i]["segments"]), np.asarray(w["segments"]))
+
+
+@pytest.mark.parametrize("rate,lens", [(44100, [44100, 30000]), (8000, [8000, 12001, 400]), (48000, [96000])])
+def test_resample_vs_torchaudio(lib, cuda, rate, lens):
+    import math
+    torchaudio = pytest.importorskip("torchaudio")
+    from sylber_b200.resample import sinc_resample_kernel, resampled_length
+    k, width, orig_g, new_g = sinc_resample_kernel(rate, 16000)
+    g = torch.Generator().manual_seed(rate)
+    B, t_in = len(lens), max(lens)
+    x = torch.zeros(B, t_in)
+    for i, n in enumerate(lens):
+        x[i, :n] = torch.randn(n, generator=g)
+    n_out = [resampled_length(n, orig_g, new_g) for n in lens]
+    t_out = max(n_out)
+    out = torch.full((B, t_out), 7.0, device=cuda)
+    n_dev = torch.zeros(B, dtype=torch.int32, device=cuda)
+    x_dev, n_in, k_dev = x.to(cuda), torch.tensor(lens, dtype=torch.int32, device=cuda), torch.from_numpy(k).to(cuda)   # keep alive
+    rc = lib.syl_resample(G.ptr(x_dev), G.ptr(n_in), B, t_in, G.ptr(k_dev), orig_g, new_g, width, G.ptr(out), G.ptr(n_dev), t_out,
+                          G.stream())
+    assert rc == 0, lib.syl_last_error(None)
+    torch.cuda.synchronize()
+    assert n_dev.cpu().tolist() == n_out
+    got = out.cpu()
+    for i, n in enumerate(lens):
+        want = torchaudio.functional.resample(x[i:i + 1, :n], rate, 16000)[0]
+        assert want.shape[0] == n_out[i]
+        assert float((got[i, :n_out[i]] - want).abs().max()) < 2e-5        # fp32 summation order only
+        assert float(got[i, n_out[i]:].abs().sum()) == 0.0
+
+
+def test_segmenter_pcm16_other_sample_rate(seg9):
+    rng = np.random.default_rng(9)
+    clips = [_pcm(rng, n) for n in (44100 * 2, 30000)]
+    want_wav, lens = frontdoor_ref.normalize_pcm16(clips, sample_rate=44100)
+    a = seg9(pcm16=clips, sample_rate=44100, in_second=False)
+    b = seg9(wav=[want_wav[i:i + 1, :lens[i]] for i in range(2)], in_second=False)
+    for x, y in zip(a, b):
+        assert x["hidden_states"].shape == y["hidden_states"].shape
+        assert _rel(x["hidden_states"], y["hidden_states"]) < 5e-4

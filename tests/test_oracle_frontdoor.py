@@ -100,3 +100,19 @@ def test_kmeans_oracle_matches_brute_force():
     idx_n, _ = frontdoor_ref.kmeans_assign(x * 3.0, c, normalize=True)
     idx_n2, _ = frontdoor_ref.kmeans_assign(x * 7.0, c, normalize=True)
     assert np.array_equal(idx_n, idx_n2)          # the normalisation removes the scale
+
+
+@pytest.mark.parametrize("rate", [44100, 48000, 8000, 22050, 11025])
+def test_resample_filter_bank_equals_torchaudio(rate):
+    """sylber_b200/resample.py restates torchaudio's sinc_interp_hann kernel (the reference calls
+    torchaudio.transforms.Resample(sr, 16000), sylber.py:85); it must be the same filter, bit for bit."""
+    import math
+    torchaudio = pytest.importorskip("torchaudio")
+    from sylber_b200.resample import sinc_resample_kernel, resampled_length
+    g = math.gcd(rate, 16000)
+    want, width = torchaudio.functional.functional._get_sinc_resample_kernel(rate, 16000, g)
+    k, w, orig_g, new_g = sinc_resample_kernel(rate, 16000)
+    assert (w, orig_g, new_g) == (width, rate // g, 16000 // g)
+    assert np.array_equal(k, want[:, 0, :].numpy())
+    x = torch.randn(1, 12345)
+    assert torchaudio.functional.resample(x, rate, 16000).shape[1] == resampled_length(12345, orig_g, new_g)
