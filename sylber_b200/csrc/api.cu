@@ -258,7 +258,7 @@ struct GemmOp {
 };
 
 struct PosOp {
-  CUtensorMap a_hi, a_lo, o_map;
+  CUtensorMap a_hi, a_lo, o_map, o_map31;
   PosConvParams p;
 };
 
@@ -558,11 +558,27 @@ int launch_gemm(syl_handle* h, const GemmOp& op, cudaStream_t st, int sm_count) 
   return SYL_OK;
 }
 
+// single-pass mode pairs taps into N = 96 MMAs (posconv.cuh); SYL_POSCONV_PAIR=0 keeps one tap per MMA (A/B timing)
+bool posconv_pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SYL_POSCONV_PAIR");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+
 int launch_posconv(syl_handle* h, const PosOp& op, cudaStream_t st, int sm_count) {
-  const int t_tiles = (op.p.T + PC_TILE_T - 1) / PC_TILE_T;
+  const bool pair = op.p.n_pass == 1 && posconv_pair_enabled();
+  const int tile_t = pair ? PC_TILE_T_PAIR : PC_TILE_T;
+  const int t_tiles = (op.p.T + tile_t - 1) / tile_t;
   const int tiles = op.p.batches * t_tiles * PC_GROUPS;
-  launch_pdl(posconv_kernel, dim3(std::min(tiles, sm_count)), dim3(PC_THREADS), PC_SMEM_TOTAL, st, op.a_hi, op.a_lo, h->pos.map_hi,
-             h->pos.map_lo, op.o_map, op.p);
+  if (pair)
+    launch_pdl(posconv_kernel<true>, dim3(std::min(tiles, sm_count)), dim3(PC_THREADS), PC_SMEM_TOTAL, st, op.a_hi, op.a_lo,
+               h->pos.map_hi, h->pos.map_lo, op.o_map, op.o_map31, op.p);
+  else
+    launch_pdl(posconv_kernel<false>, dim3(std::min(tiles, sm_count)), dim3(PC_THREADS), PC_SMEM_TOTAL, st, op.a_hi, op.a_lo,
+               h->pos.map_hi, h->pos.map_lo, op.o_map, op.o_map31, op.p);
   CUDA_TRY(h, cudaGetLastError());
   return SYL_OK;
 }
@@ -571,7 +587,8 @@ bool g_attrs_set = false;
 int ensure_attrs(syl_handle* h) {
   if (g_attrs_set) return SYL_OK;
   CUDA_TRY(h, cudaFuncSetAttribute(gemm3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL));
-  CUDA_TRY(h, cudaFuncSetAttribute(posconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM_TOTAL));
+  CUDA_TRY(h, cudaFuncSetAttribute(posconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM_TOTAL));
+  CUDA_TRY(h, cudaFuncSetAttribute(posconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM_TOTAL));
   CUDA_TRY(h, (cudaFuncSetAttribute(attention7_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL)));
   CUDA_TRY(h, (cudaFuncSetAttribute(attention7_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL)));
   CUDA_TRY(h, (cudaFuncSetAttribute(attention7_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL)));
@@ -662,6 +679,7 @@ int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
     if (!make_tmap_f16(&op.a_hi, at<__half>(ws, L.h16_hi), 3, dims, str, PC_WIN_ROWS / 2, &h->err)) return SYL_E_CUDA;
     if (!make_tmap_f16(&op.a_lo, at<__half>(ws, L.h16_lo), 3, dims, str, PC_WIN_ROWS / 2, &h->err)) return SYL_E_CUDA;
     if (!make_tmap(&op.o_map, at<float>(ws, L.pos), 4, 3, dims, str, 16, 32, 64, &h->err)) return SYL_E_CUDA;
+    if (!make_tmap(&op.o_map31, at<float>(ws, L.pos), 4, 3, dims, str, 16, 31, 64, &h->err)) return SYL_E_CUDA;
     op.p.T = T;
     op.p.batches = batch;
     op.p.n_pass = split_pos ? 3 : 1;

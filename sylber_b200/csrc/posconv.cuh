@@ -12,6 +12,14 @@
 //
 //   warp 0 : TMA producer (window + weight ring)      warp 1 : MMA issuer (128 taps x 2 M-tiles x passes x 3 k-steps)
 //   warp 2 : TMEM allocator                            warps 4..11 : epilogue (bias + GELU, TMA store of fp32)
+//
+// Tap pairs (kPair, the single-pass mode).  The issuing thread, not the tensor core, bounds this kernel: an N = 48 MMA
+// is 24 cycles of math but ~90 cycles of issue + dispatch here (ncu: tensor pipe 31 % active).  So two taps share one
+// MMA: the B operand is [W_j ; W_{j+1}] (N = 96, adjacent halves of a ring stage) against the window shifted by the
+// EVEN tap j.  Columns 0..47 then hold D[r] = sum_{j even} W_j x[r + j], columns 48..95 hold
+// E[r] = sum_{j even} W_{j+1} x[r + j], and since the odd taps need x[r + j + 1],  out[r] = D[r] + E[r + 1].
+// The epilogue fetches E[r + 1] from the neighbouring row through shared memory; a CTA tile therefore yields 255
+// output frames (row 255 has no E[256]) and tiles advance by 255 frames.  Half the MMAs, half the window re-reads.
 #pragma once
 
 #include "common.cuh"
@@ -22,6 +30,7 @@ constexpr int PC_TAPS = 128;
 constexpr int PC_CG = 48;                  // channels per group
 constexpr int PC_GROUPS = 16;
 constexpr int PC_TILE_T = 256;             // frames per CTA tile (2 MMA M-tiles)
+constexpr int PC_TILE_T_PAIR = 255;        // output frames per CTA tile in tap-pair mode
 constexpr int PC_WIN_ROWS = 384;           // window rows: 64 left halo + 256 + 63 right halo, rounded up
 constexpr int PC_WIN_BYTES = PC_WIN_ROWS * 128;      // 48 KB (64 fp16 columns per row, 48 used)
 constexpr int PC_W_BYTES = PC_CG * 128;              // 6 KB per tap
@@ -53,10 +62,12 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128_shifted(uint32_t smem_addr
   return d;
 }
 
+template <bool kPair>
 __global__ void __launch_bounds__(PC_THREADS, 1)
 posconv_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__ CUtensorMap a_lo,
                const __grid_constant__ CUtensorMap w_hi, const __grid_constant__ CUtensorMap w_lo,
-               const __grid_constant__ CUtensorMap o_map, const PosConvParams p) {
+               const __grid_constant__ CUtensorMap o_map, const __grid_constant__ CUtensorMap o_map31,
+               const PosConvParams p) {
   griddep_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -70,9 +81,10 @@ posconv_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6 + 2 * PC_W_STAGES);
 
   const int warp = threadIdx.x >> 5;
-  const int t_tiles = (p.T + PC_TILE_T - 1) / PC_TILE_T;
+  constexpr int kTileT = kPair ? PC_TILE_T_PAIR : PC_TILE_T;
+  const int t_tiles = (p.T + kTileT - 1) / kTileT;
   const int num_tiles = p.batches * t_tiles * PC_GROUPS;
-  const bool split = p.n_pass == 3;
+  const bool split = !kPair && p.n_pass == 3;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&a_hi);
@@ -108,7 +120,7 @@ posconv_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__
         const int g = tile % PC_GROUPS;
         const int tt = (tile / PC_GROUPS) % t_tiles;
         const int b = tile / (PC_GROUPS * t_tiles);
-        const int row0 = tt * PC_TILE_T - PC_TAPS / 2;
+        const int row0 = tt * kTileT - PC_TAPS / 2;
         mbar_wait(win_empty, win_phase ^ 1);
         mbar_arrive_expect_tx(win_full, split ? 2 * PC_WIN_BYTES : PC_WIN_BYTES);
         tma_load_3d(smem + PC_SMEM_WIN_HI, &a_hi, win_full, g * PC_CG, row0, b);
@@ -118,12 +130,13 @@ posconv_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__
           tma_load_3d(smem + PC_SMEM_WIN_LO + PC_WIN_BYTES / 2, &a_lo, win_full, g * PC_CG, row0 + PC_WIN_ROWS / 2, b);
         }
         win_phase ^= 1;
-        for (int tap = 0; tap < PC_TAPS; ++tap) {
+        for (int tap = 0; tap < PC_TAPS; tap += (kPair ? 2 : 1)) {
           mbar_wait(&w_empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&w_full[stage], split ? 2 * PC_W_BYTES : PC_W_BYTES);
+          mbar_arrive_expect_tx(&w_full[stage], (split || kPair) ? 2 * PC_W_BYTES : PC_W_BYTES);
           uint8_t* ws = smem + PC_SMEM_W + stage * 2 * PC_W_BYTES;
           tma_load_2d(ws, &w_hi, &w_full[stage], tap * 64, g * PC_CG);
           if (split) tma_load_2d(ws + PC_W_BYTES, &w_lo, &w_full[stage], tap * 64, g * PC_CG);
+          if (kPair) tma_load_2d(ws + PC_W_BYTES, &w_hi, &w_full[stage], (tap + 1) * 64, g * PC_CG);   // [W_j ; W_{j+1}]
           if (++stage == PC_W_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -151,11 +164,11 @@ posconv_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__
         mbar_wait(win_full, win_phase);
         win_phase ^= 1;
         tc_fence_after_sync();
-        for (int tap = 0; tap < PC_TAPS; ++tap) {
+        for (int tap = 0; tap < PC_TAPS; tap += (kPair ? 2 : 1)) {
           mbar_wait(&w_full[stage], phase);
           tc_fence_after_sync();
           const uint32_t wb = smem_u32(smem + PC_SMEM_W + stage * 2 * PC_W_BYTES);
-          const uint64_t bd_hi = make_desc_k_sw128(wb);      // [W_hi ; W_lo]: 96 rows when split, 48 otherwise
+          const uint64_t bd_hi = make_desc_k_sw128(wb);      // [W_hi ; W_lo] (split) or [W_j ; W_{j+1}] (pair): 96 rows, else 48
 #pragma unroll
           for (int m = 0; m < 2; ++m) {
             const uint32_t tmem_d = tmem_base + acc * 256 + m * 128;
@@ -167,6 +180,9 @@ posconv_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__
               for (int k = 0; k < 3; ++k) umma_f16_ss(tmem_d, ad_hi + 2 * k, bd_hi + 2 * k, idesc96, (tap | k) != 0);
 #pragma unroll
               for (int k = 0; k < 3; ++k) umma_f16_ss(tmem_d, ad_lo + 2 * k, bd_hi + 2 * k, idesc, 1);
+            } else if (kPair) {
+#pragma unroll
+              for (int k = 0; k < 3; ++k) umma_f16_ss(tmem_d, ad_hi + 2 * k, bd_hi + 2 * k, idesc96, (tap | k) != 0);
             } else {
 #pragma unroll
               for (int k = 0; k < 3; ++k) umma_f16_ss(tmem_d, ad_hi + 2 * k, bd_hi + 2 * k, idesc, (tap | k) != 0);
@@ -202,8 +218,13 @@ posconv_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__
       const int g = tile % PC_GROUPS;
       const int tt = (tile / PC_GROUPS) % t_tiles;
       const int b = tile / (PC_GROUPS * t_tiles);
-      const int warp_row0 = tt * PC_TILE_T + m * 128 + quarter * 32;
+      const int warp_row0 = tt * kTileT + m * 128 + quarter * 32;
       const bool warp_ok = warp_row0 < p.T;
+      // tap-pair mode: rows exchange their E halves through the (unused) lo-window region, one 16 KB slab per column
+      // chunk; the barrier keeps this tile's writes behind the previous tile's reads
+      const int R = m * 128 + quarter * 32 + lane;                 // row inside the CTA tile
+      const uint32_t xbuf = smem_u32(smem + PC_SMEM_WIN_LO);
+      if (kPair) named_bar_sync(1, 256);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + m * 128);
@@ -211,14 +232,29 @@ posconv_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__
       for (int c = 0; c < 3; ++c) {
         uint32_t r[16], r2[16];
         tmem_ld_32x32b_x16(taddr + c * 16, r);
-        if (split) tmem_ld_32x32b_x16(taddr + PC_CG + c * 16, r2);     // the A_hi * W_lo half
+        if (split || kPair) tmem_ld_32x32b_x16(taddr + PC_CG + c * 16, r2);     // the A_hi * W_lo half / the odd-tap half E
         tmem_ld_wait();
+        if (kPair) {
+          // E[R] -> shared memory (64-byte rows, 16-byte chunks XOR-swizzled by (row >> 1) & 3), then read E[R + 1]
+          const uint32_t slab = xbuf + c * 16384;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            st_shared_v4(slab + R * 64 + ((i ^ ((R >> 1) & 3)) << 4), r2[4 * i], r2[4 * i + 1], r2[4 * i + 2], r2[4 * i + 3]);
+          named_bar_sync(2, 256);
+          const int Rn = min(R + 1, 255);                          // row 255 is never stored
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t a = slab + Rn * 64 + ((i ^ ((Rn >> 1) & 3)) << 4);
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(r2[4 * i]), "=r"(r2[4 * i + 1]), "=r"(r2[4 * i + 2]), "=r"(r2[4 * i + 3]) : "r"(a));
+          }
+        }
         const int col0 = g * PC_CG + c * 16;
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           float acc_v = __uint_as_float(r[i]);
-          if (split) acc_v += __uint_as_float(r2[i]);
+          if (split || kPair) acc_v += __uint_as_float(r2[i]);
           v[i] = acc_v + __ldg(p.bias + col0 + i);
         }
 #pragma unroll
@@ -232,7 +268,8 @@ posconv_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_3d(&o_map, stage_buf, col0, warp_row0, b);
+            // tap-pair mode: the tile's last warp stores 31 rows (row 255 belongs to the next tile)
+            tma_store_3d((kPair && m == 1 && quarter == 3) ? &o_map31 : &o_map, stage_buf, col0, warp_row0, b);
             tma_store_commit();
           }
         }

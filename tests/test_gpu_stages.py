@@ -92,3 +92,29 @@ def test_stage_entry_points_reject_bad_arguments(setup):
     assert eng.lib.syl_conv_frontend(eng.handle, G.ptr(x), 1, 100, G.ptr(x), G.ptr(x), 8, G.stream()) != 0
     need = int(eng.lib.syl_workspace_bytes(eng.handle, 2, 16000))
     assert eng.lib.syl_conv_frontend(eng.handle, G.ptr(x), 2, 16000, G.ptr(x), G.ptr(x), need - 1, G.stream()) == -4   # SYL_E_WORKSPACE
+
+
+@pytest.mark.parametrize("n", [48000, 160000, 82000])
+def test_positional_conv_stage_vs_oracle(setup, n):
+    """The single-pass positional conv pairs taps into N = 96 MMAs and exchanges half results between neighbouring
+    rows (posconv.cuh); checked here at tile boundaries (T = 149, 499, 255 + 1) against the oracle's pos stage."""
+    from oracle.hubert_ref import hubert_forward
+    sd, seg = setup
+    eng = seg._engine
+    g = torch.Generator().manual_seed(n)
+    wav = torch.randn(2, n, generator=g)
+    lens = [n, n - 5000]
+    wav[1, lens[1]:] = 0
+    stages = {}
+    hubert_forward(sd, wav, lens, 9, stages=stages)
+    T = num_frames(n)
+    st = torch.cuda.Stream(); torch.cuda.set_stream(st)
+    eng.forward(wav.to(eng.device), torch.tensor(lens, dtype=torch.int32, device=eng.device), 2.6, 0.8, segment=False, slot="stage_test")
+    got = eng.read_stage("pos", (2, T, 768)).cpu().numpy()
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(torch.cuda.default_stream())
+    want = stages["pos"].numpy()
+    assert _rel(got, want) < 1e-3
+    # row-wise: no frame may be off (a wrong neighbour exchange would corrupt single rows, not the norm)
+    row_err = np.linalg.norm(got - want, axis=-1) / (np.linalg.norm(want, axis=-1) + 1e-6)
+    assert row_err.max() < 5e-3, (row_err.argmax(), row_err.max())
