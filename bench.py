@@ -309,8 +309,9 @@ def run_ours(args):
         stages["conv0_gn_gelu"].update({"bound": "hbm", "achieved_gbs": round(gbs, 1), "frac": round(gbs / peaks["hbm_gbs"], 4)})
     if "layernorm" in stages:
         M = B * T
-        # LN(512): fp32 in, fp16 hi (+ lo) out; every LN(768): two fp32 inputs (GEMM output + residual), fp32 + fp16 hi out
-        by = M * 512 * (4 + (4 if args.mode != "fast" else 2)) + (1 + 2 * layers) * M * 768 * (4 + 4 + 4 + 2)
+        # LN(512): fp32 in, fp16 hi (+ lo) out; LN(768): fp32 GEMM output + residual (fp16 hi + lo pair; fp32 for the
+        # post-pos-conv one) in, fp16 pair out; the last one also writes the fp32 hidden states
+        by = M * 512 * (4 + (4 if args.mode != "fast" else 2)) + (1 + 2 * layers) * M * 768 * (4 + 4 + 4) + M * 768 * 4
         gbs = by / (stages["layernorm"]["ms_per_step"] * 1e-3) / 1e9
         stages["layernorm"].update({"bound": "hbm", "achieved_gbs": round(gbs, 1), "frac": round(gbs / peaks["hbm_gbs"], 4)})
     if "attention" in stages:

@@ -752,10 +752,11 @@ int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
 }
 
 template <int D>
-void launch_ln(const float* x, const float* add, const float* g, const float* b, int rows, float* of, __half* ohi,
-               __half* olo, cudaStream_t st) {
+void launch_ln(const float* x, const float* add, const __half* add_hi, const __half* add_lo, const float* g, const float* b, int rows,
+               float* of, __half* ohi, __half* olo, cudaStream_t st) {
   const int warps = 8;
-  launch_pdl(layernorm_rows_kernel<D>, dim3((rows + warps - 1) / warps), dim3(warps * 32), 0, st, x, add, g, b, rows, of, ohi, olo);
+  launch_pdl(layernorm_rows_kernel<D>, dim3((rows + warps - 1) / warps), dim3(warps * 32), 0, st, x, add, add_hi, add_lo, g, b, rows, of,
+             ohi, olo);
 }
 
 long long* g_attn_trace = nullptr;   // set by syl_attention_trace for one launch
@@ -852,9 +853,9 @@ int run_layer(syl_handle* h, int l, float* h_out, cudaStream_t st) {
     if ((rc = launch_gemm(h, pl.out[l], st, h->sm_count))) return rc;
   }
   {
-    StageTimer tm(h, ST_LN, st);   // h = LN(h + attn)
-    launch_ln<kH>(at<float>(ws, L.pre), at<float>(ws, L.h), w.ln1_g, w.ln1_b, M, at<float>(ws, L.h), at<__half>(ws, L.h16_hi),
-                  split_enc ? at<__half>(ws, L.h16_lo) : nullptr, st);
+    StageTimer tm(h, ST_LN, st);   // h = LN(h + attn); the residual stream is the fp16 pair (h16_hi, h16_lo), in place
+    launch_ln<kH>(at<float>(ws, L.pre), nullptr, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), w.ln1_g, w.ln1_b, M, nullptr,
+                  at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), st);
   }
   {
     StageTimer tm(h, ST_FFN1, st);
@@ -865,9 +866,9 @@ int run_layer(syl_handle* h, int l, float* h_out, cudaStream_t st) {
     if ((rc = launch_gemm(h, pl.ffn2[l], st, h->sm_count))) return rc;
   }
   {
-    StageTimer tm(h, ST_LN, st);   // h = LN(h + ffn)
-    launch_ln<kH>(at<float>(ws, L.pre), at<float>(ws, L.h), w.ln2_g, w.ln2_b, M, h_out, at<__half>(ws, L.h16_hi),
-                  split_enc ? at<__half>(ws, L.h16_lo) : nullptr, st);
+    StageTimer tm(h, ST_LN, st);   // h = LN(h + ffn); fp32 only where the caller wants the layer output (h_out)
+    launch_ln<kH>(at<float>(ws, L.pre), nullptr, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), w.ln2_g, w.ln2_b, M, h_out,
+                  at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), st);
   }
   CUDA_TRY(h, cudaGetLastError());
   return SYL_OK;
@@ -1070,7 +1071,7 @@ static int enqueue_forward(syl_handle* h, Plan& pl, const float* wav, const int3
   if ((rc = run_frontend(h, wav, st))) return rc;
   {
     StageTimer tm(h, ST_LN, st);
-    launch_ln<kC>(at<float>(workspace, L.conv6), nullptr, h->fp_ln_g, h->fp_ln_b, M, nullptr, at<__half>(workspace, L.ln_hi),
+    launch_ln<kC>(at<float>(workspace, L.conv6), nullptr, nullptr, nullptr, h->fp_ln_g, h->fp_ln_b, M, nullptr, at<__half>(workspace, L.ln_hi),
                   split_proj ? at<__half>(workspace, L.ln_lo) : nullptr, st);
   }
   {
@@ -1085,14 +1086,13 @@ static int enqueue_forward(syl_handle* h, Plan& pl, const float* wav, const int3
   // h = LN(h + pos)   (modeling_hubert.py:441-442); with zero layers this is already the output
   {
     StageTimer tm(h, ST_LN, st);
-    launch_ln<kH>(at<float>(workspace, L.h), at<float>(workspace, L.pos), h->enc_ln_g, h->enc_ln_b, M,
-                  nl == 0 ? hidden : at<float>(workspace, L.h), at<__half>(workspace, L.h16_hi),
-                  split_enc ? at<__half>(workspace, L.h16_lo) : nullptr, st);
+    launch_ln<kH>(at<float>(workspace, L.h), at<float>(workspace, L.pos), nullptr, nullptr, h->enc_ln_g, h->enc_ln_b, M,
+                  nl == 0 ? hidden : nullptr, at<__half>(workspace, L.h16_hi), at<__half>(workspace, L.h16_lo), st);
   }
   CUDA_TRY(h, cudaGetLastError());
   for (int l = 0; l < nl; ++l) {
-    float* out = (l == nl - 1) ? hidden : at<float>(workspace, L.h);
-    // the residual for FFN2 must be the post-attention LN output, which run_layer keeps in workspace h
+    // between layers the residual stream exists only as the fp16 pair (h16_hi, h16_lo); the last layer also writes fp32
+    float* out = (l == nl - 1) ? hidden : nullptr;
     if ((rc = run_layer(h, l, out, st))) return rc;
   }
   if (seg) {
@@ -1445,7 +1445,11 @@ int syl_read_stage(syl_handle* h, const char* name, float* out, size_t n_floats,
   if (s == "conv6") { src = at<float>(pl.ws, L.conv6); n = M * kC; }
   else if (s == "pos") { src = at<float>(pl.ws, L.pos); n = M * kH; }
   else if (s == "pre") { src = at<float>(pl.ws, L.pre); n = M * kH; }
-  else if (s == "h") { src = at<float>(pl.ws, L.h); n = M * kH; }
+  else if (s == "h") {      // the residual stream lives as an fp16 pair
+    if (n_floats < M * kH) return fail(h, SYL_E_ARG, "syl_read_stage: output too small");
+    join_f16_kernel<<<grid_for(M * kH), 256, 0, st>>>(at<__half>(pl.ws, L.h16_hi), at<__half>(pl.ws, L.h16_lo), out, M * kH);
+    return SYL_OK;
+  }
   else return fail(h, SYL_E_ARG, "syl_read_stage: unknown stage '%s'", name);
   if (n_floats < n) return fail(h, SYL_E_ARG, "syl_read_stage: output too small (%zu < %zu)", n_floats, n);
   CUDA_TRY(h, cudaMemcpyAsync(out, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
