@@ -505,15 +505,17 @@ class Segmenter:
         results = [None] * len(rows)
 
         def collect(item):
-            st, idx, hidden_h, hidden_pin, seg, cnt_pin, feat = item
-            st.synchronize()
+            st, idx, hidden_h, hidden_pin, seg_pin, cnt_pin, feat, ev = item
+            # the segment table travels first (it is tiny), so the number of segments is known on the host while the
+            # hidden states are still in flight and the feature copy queues right behind them: one wait, not three
+            ev.synchronize()
             cnt_h = cnt_pin.numpy()
             n_max = max(int(cnt_h.max()) if len(cnt_h) else 0, 1)
             with torch.cuda.stream(st):
-                seg_h = seg[:, :n_max].cpu().numpy()
                 feat_h, feat_pin = eng.pool.array((len(idx), n_max, HIDDEN))
                 feat_pin.copy_(feat[:, :n_max], non_blocking=True)
             st.synchronize()
+            seg_h = seg_pin.numpy()
             del hidden_pin, feat_pin
             for i, r in enumerate(idx):
                 n = int(cnt_h[i])
@@ -536,11 +538,15 @@ class Segmenter:
                 else:
                     wav_dev, n_dev = eng.upload(chunk, sub_len, max_length, slot)
                 hidden, seg, cnt, feat = eng.forward(wav_dev, n_dev, thr_n, thr_m, slot=slot)
-                hidden_h, hidden_pin = eng.pool.array(tuple(hidden.shape))
-                hidden_pin.copy_(hidden, non_blocking=True)
                 cnt_pin = torch.empty(cnt.shape, dtype=torch.int32, pin_memory=True)
                 cnt_pin.copy_(cnt, non_blocking=True)
-            pending[slot] = (st, idx, hidden_h, hidden_pin, seg, cnt_pin, feat)
+                seg_pin = torch.empty(seg.shape, dtype=torch.int32, pin_memory=True)     # fixed-stride table: B x T x 2 int32
+                seg_pin.copy_(seg, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(st)
+                hidden_h, hidden_pin = eng.pool.array(tuple(hidden.shape))
+                hidden_pin.copy_(hidden, non_blocking=True)
+            pending[slot] = (st, idx, hidden_h, hidden_pin, seg_pin, cnt_pin, feat, ev)
         # collect in launch order: the oldest sub-batch finishes first
         n_w = len(work)
         for k in range(max(0, n_w - len(streams)), n_w):
