@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .batching import plan_length_buckets
+from .batching import plan_length_buckets, sub_batch_bounds
 from .resample import sinc_resample_kernel, resampled_length
 from .weights import normalize_state_dict, random_hubert_state_dict, REQUIRED_KEYS
 
@@ -462,29 +462,8 @@ class Segmenter:
 
     # ------------------------------------------------------------------------------------------
     def _sub_batches(self, n_rows):
-        """(lo, hi) sub-batch bounds of one padded batch of n_rows rows."""
-        n_sub = max(1, min(self.streams, n_rows // 8)) if n_rows <= self.max_batch else 1
-        bounds = []
-        if self.sub_batch_sizes and sum(self.sub_batch_sizes) == n_rows:       # explicit split (experiments)
-            a = 0
-            for k in self.sub_batch_sizes:
-                bounds.append((a, a + k))
-                a += k
-            return bounds
-        for lo in range(0, n_rows, self.max_batch):
-            hi = min(lo + self.max_batch, n_rows)
-            # the LAST sub-batch's device->host copy is the one nothing overlaps, so it gets 2/3 of an even share
-            # (32 rows, 3 streams -> 12, 12, 8: measured 6.08 ms against 6.40 ms for 11, 11, 10)
-            n = hi - lo
-            sizes = [int(round(n / (n_sub - 1 / 3)))] * (n_sub - 1) if n_sub > 1 else []
-            sizes.append(n - sum(sizes))
-            if min(sizes) <= 0:
-                sizes = [n]
-            a = lo
-            for k in sizes:
-                bounds.append((a, a + k))
-                a += k
-        return bounds
+        """(lo, hi) sub-batch bounds of one padded batch of n_rows rows (batching.sub_batch_bounds)."""
+        return sub_batch_bounds(n_rows, self.streams, self.max_batch, self.sub_batch_sizes)
 
     def _run_jobs(self, rows, lengths, jobs, pcm=0):
         """Padded batches through the engine.  rows: 1-D fp32 CPU tensors (or int16 at `pcm` Hz when pcm != 0); jobs: list of

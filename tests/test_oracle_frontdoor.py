@@ -116,3 +116,30 @@ def test_resample_filter_bank_equals_torchaudio(rate):
     assert np.array_equal(k, want[:, 0, :].numpy())
     x = torch.randn(1, 12345)
     assert torchaudio.functional.resample(x, rate, 16000).shape[1] == resampled_length(12345, orig_g, new_g)
+
+
+def test_sub_batch_bounds_cover_every_row_once():
+    from sylber_b200.batching import sub_batch_bounds
+    for n in list(range(1, 70)) + [100, 256]:
+        for streams in (1, 2, 3, 4):
+            for max_batch in (32, 64):
+                b = sub_batch_bounds(n, streams, max_batch)
+                assert b[0][0] == 0 and b[-1][1] == n
+                assert all(lo < hi for lo, hi in b) and all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
+                assert all(hi - lo <= max_batch for lo, hi in b)
+                if n <= max_batch:
+                    assert len(b) <= streams
+    assert [hi - lo for lo, hi in sub_batch_bounds(32, 3, 32)] == [12, 12, 8]
+    assert [hi - lo for lo, hi in sub_batch_bounds(7, 3, 32)] == [7]
+    assert [hi - lo for lo, hi in sub_batch_bounds(80, 3, 32)] == [32, 32, 16]
+    assert sub_batch_bounds(32, 3, 32, explicit=[16, 16]) == [(0, 16), (16, 32)]
+    assert [hi - lo for lo, hi in sub_batch_bounds(32, 3, 32, explicit=[5, 5])] == [12, 12, 8]      # wrong sum: rule applies
+
+
+def test_resampled_length_matches_ceil():
+    import math
+    from sylber_b200.resample import resampled_length
+    for rate in (8000, 11025, 22050, 44100, 48000):
+        g = math.gcd(rate, 16000)
+        for n in (1, 2, 399, 400, 12345, 441000):
+            assert resampled_length(n, rate // g, 16000 // g) == math.ceil(16000 * n / rate)
