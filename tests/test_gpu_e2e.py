@@ -176,3 +176,25 @@ def test_long_form_60s(seg9):
     ref = hubert_forward(syllabic_test_state_dict(9, 0), wav, [960000], 9).numpy()
     assert _rel(out["hidden_states"], ref[0]) < TOL
     _check_against_own_states(out)
+
+
+def test_twelve_layer_encoder_vs_oracle():
+    """BASELINE.json names the 12-layer hubert-base encoder (the reference checkpoint keeps 9): same path, n_layers = 12,
+    on a padded 3-clip batch against the CPU oracle, in every precision preset."""
+    sd = syllabic_test_state_dict(12, 1)
+    gen = torch.Generator().manual_seed(12)
+    lens = [40000, 27000, 16000]
+    wavs = [torch.randn(1, n, generator=gen) for n in lens]
+    batch = torch.zeros(3, max(lens))
+    for i, w in enumerate(wavs):
+        batch[i, :lens[i]] = w[0]
+    ref = hubert_forward(sd, batch, lens, 12).numpy()
+    for mode, bar in (("parity", TOL), ("fast", TOL), ("exact", 1e-4)):
+        seg = Segmenter(model_ckpt=None, state_dict=sd, encoding_layer=12, device="cuda:0", mode=mode)
+        outs = seg(wav=wavs, in_second=False)
+        assert seg.speech_model.config.num_hidden_layers == 12
+        for i, o in enumerate(outs):
+            assert o["hidden_states"].shape == ref[i].shape
+            assert _rel(o["hidden_states"], ref[i]) < bar, (mode, i)
+            _check_against_own_states(o)
+        del seg
