@@ -34,6 +34,20 @@ def normalize_pcm16(pcm_list, normalize=True, sample_rate=16000):
     return out, lens
 
 
+def resample_f64(x, sample_rate):
+    """Band-limited sinc resampling to 16 kHz in float64: the reference's torchaudio.transforms.Resample (sylber.py:85)
+    restated from its filter bank (sylber_b200/resample.py, bit-identical to torchaudio's - tests/test_oracle_frontdoor.py)
+    and evaluated exactly; torchaudio's own fp32 conv1d is ~1e-5 away from this on unit-variance input."""
+    from sylber_b200.resample import sinc_resample_kernel, resampled_length
+    h, width, orig_g, new_g = sinc_resample_kernel(sample_rate, 16000)
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    K = h.shape[1]
+    xpad = np.concatenate([np.zeros(width), x, np.zeros(width + orig_g)])
+    win = np.lib.stride_tricks.sliding_window_view(xpad, K)[::orig_g]            # [blocks, K]
+    y = (win @ h.astype(np.float64).T).reshape(-1)                               # [blocks * new_g]
+    return y[:resampled_length(len(x), orig_g, new_g)]
+
+
 def kmeans_assign(feats, centroids, normalize=False):
     x = np.asarray(feats, dtype=np.float64).reshape(-1, centroids.shape[1])
     if normalize:

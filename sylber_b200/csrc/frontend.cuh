@@ -248,8 +248,11 @@ conv0_mma_kernel(const float* __restrict__ wav, int t_samp, int L0, const uint4*
 // fp32), so a LayerNorm call moves 12 bytes per element (fp32 GEMM output + pair in, pair out) instead of 14.
 // (Two rows per warp - one resident wave of warps, twice the loads in flight - was measured slower: 0.78 vs 0.64 ms.)
 // ----------------------------------------------------------------------------------------------
+// __launch_bounds__(256, 4): the 64-register allocation this asks for schedules all row loads up front; the kernel is
+// latency bound, and 0.65 -> 0.575 ms per step against the 59-register default (40 / 32 registers with 6 / 8 blocks
+// per SM spill and are slower: 0.65 / 0.75 ms; profiles/r02_bench_ab.md)
 template <int D>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ add, const __half* add_hi, const __half* add_lo,
                       const float* __restrict__ gamma, const float* __restrict__ beta, int rows, float* __restrict__ out_f32,
                       __half* out_hi, __half* out_lo) {

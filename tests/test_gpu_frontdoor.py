@@ -160,15 +160,23 @@ def test_resample_vs_torchaudio(lib, cuda, rate, lens):
                           G.stream())
     assert rc == 0, lib.syl_last_error(None)
     torch.cuda.synchronize()
-    assert n_dev.cpu().tolist() == n_out
+    assert n_dev.cpu().tolist() == n_out, (n_dev.cpu().tolist(), n_out)
     got = out.cpu()
     for i, n in enumerate(lens):
+        # oracle: the same filter bank evaluated in float64 (pinned against torchaudio on the CPU side); the kernel's
+        # fp32 FMA chain over up to 475 taps stays within a few 1e-6 of it.  torchaudio's own fp32 result is a second
+        # fp32 implementation (~1e-5 from the exact sum), so it only gets a loose bound here.
+        exact = frontdoor_ref.resample_f64(x[i, :n].numpy(), rate)
+        assert exact.shape[0] == n_out[i]
+        diff = np.abs(got[i, :n_out[i]].numpy().astype(np.float64) - exact)
+        j = int(diff.argmax())
+        # (the message carries the evidence: this test failed in 2 of ~10 full-suite runs in round 2, never in isolation,
+        # with the kernel's arithmetic 4e-7 from the exact sum in emulation - see profiles/r02_next_steps.md)
+        assert diff[j] < 2e-5, f"clip {i}: |gpu - exact| = {diff[j]:.3e} at sample {j} of {n_out[i]} (gpu {got[i, j]:.6f}, exact {exact[j]:.6f}); " \
+                               f"{int((diff > 2e-5).sum())} samples off"
         want = torchaudio.functional.resample(x[i:i + 1, :n], rate, 16000)[0]
-        assert want.shape[0] == n_out[i]
-        # fp32 summation order only: torchaudio's own fp32 conv1d is up to 1.0e-5 away from the float64 result on this
-        # input (475 taps, |y| up to 2.3), and so is the kernel's sequential FMA chain
-        assert float((got[i, :n_out[i]] - want).abs().max()) < 5e-5
-        assert float(got[i, n_out[i]:].abs().sum()) == 0.0
+        assert float((got[i, :n_out[i]] - want).abs().max()) < 1e-4
+        assert float(got[i, n_out[i]:].abs().sum()) == 0.0, f"clip {i}: tail not zero"
 
 
 def test_segmenter_pcm16_other_sample_rate(seg9):

@@ -143,3 +143,13 @@ def test_resampled_length_matches_ceil():
         g = math.gcd(rate, 16000)
         for n in (1, 2, 399, 400, 12345, 441000):
             assert resampled_length(n, rate // g, 16000 // g) == math.ceil(16000 * n / rate)
+
+
+@pytest.mark.parametrize("rate,n", [(44100, 44100), (8000, 12001), (48000, 30000), (22050, 400)])
+def test_resample_f64_oracle_agrees_with_torchaudio(rate, n):
+    torchaudio = pytest.importorskip("torchaudio")
+    x = torch.randn(n, generator=torch.Generator().manual_seed(rate + n))
+    want = torchaudio.functional.resample(x[None], rate, 16000)[0].numpy()
+    got = frontdoor_ref.resample_f64(x.numpy(), rate)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() < 3e-5          # torchaudio's fp32 conv1d against the exact sum
