@@ -174,8 +174,10 @@ def test_resample_vs_torchaudio(lib, cuda, rate, lens):
         # with the kernel's arithmetic 4e-7 from the exact sum in emulation - see profiles/r02_next_steps.md)
         assert diff[j] < 2e-5, f"clip {i}: |gpu - exact| = {diff[j]:.3e} at sample {j} of {n_out[i]} (gpu {got[i, j]:.6f}, exact {exact[j]:.6f}); " \
                                f"{int((diff > 2e-5).sum())} samples off"
+        # torchaudio's conv1d is whatever fp32 kernel oneDNN picks for the host CPU, and the boxes differ: only gross errors
+        # (a wrong phase or tap) are checked against it here; tests/test_oracle_frontdoor.py pins the oracle to it
         want = torchaudio.functional.resample(x[i:i + 1, :n], rate, 16000)[0]
-        assert float((got[i, :n_out[i]] - want).abs().max()) < 1e-4
+        assert float((got[i, :n_out[i]] - want).abs().max()) < 1e-3
         assert float(got[i, n_out[i]:].abs().sum()) == 0.0, f"clip {i}: tail not zero"
 
 
