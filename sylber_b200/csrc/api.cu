@@ -320,6 +320,8 @@ struct syl_handle {
   int plan_cur = 0;
   uint64_t plan_clock = 0;
   int sm_count = 148;
+  uint8_t* sk_pool = nullptr;   // stream-K scratch (gemm3_tc.cuh), one area per plan; null unless SYL_STREAMK=1
+  size_t sk_area = 0;
   bool profile = false;
   bool use_graphs = true;
   std::vector<ProfRec> recs;
@@ -541,19 +543,62 @@ bool make_o_maps(syl_handle* h, GemmOp& op, float* f32, __half* hi, __half* lo, 
   return true;
 }
 
-int launch_gemm3_raw(const GemmOp& op, const CUtensorMap& b_hi, const CUtensorMap& b_lo, cudaStream_t st, int sm_count) {
-  const GemmParams& p = op.p;
+// Stream-K schedule of the GEMM (gemm3_tc.cuh).  Off by default: written at the end of round 1 after the GPU budget
+// was spent, never run on a GPU yet.  SYL_STREAMK=1 allocates the scratch pool at finalize and uses the schedule for
+// GEMMs whose last round of whole tiles leaves at least SYL_STREAMK_PCT percent (default 4) of the cluster slots idle.
+bool streamk_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SYL_STREAMK");
+    v = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+int streamk_min_idle_pct() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SYL_STREAMK_PCT");
+    v = e ? std::max(0, atoi(e)) : 4;
+  }
+  return v;
+}
+constexpr size_t kSkHeaderBytes = 16384;   // ticket at byte 0, flags from byte 256 (74 clusters x 32 flags x 4 B)
+size_t streamk_area_bytes(int sm_count) { return kSkHeaderBytes + (size_t)(sm_count / 2) * GEMM3_SK_SLOT_FLOATS * sizeof(float); }
+// does the stream-K schedule apply?  Needs every cluster's share to be at least one tile (so no item is cut on both
+// sides) and all clusters of the persistent grid; pays when the last data-parallel round is badly filled.
+bool gemm_streamk_wanted(int tiles, int clusters, int sm_count) {
+  if (!streamk_enabled() || pdl_enabled()) return false;
+  if (clusters != sm_count / 2 || tiles <= clusters) return false;
+  if ((size_t)clusters * GEMM3_SK_FLAGS_PER_CLUSTER * sizeof(unsigned) + 256 > kSkHeaderBytes) return false;
+  const int rounds = (tiles + clusters - 1) / clusters;
+  const int idle = rounds * clusters - tiles;
+  return idle * 100 >= streamk_min_idle_pct() * rounds * clusters;
+}
+
+int launch_gemm3_raw(const GemmOp& op, const CUtensorMap& b_hi, const CUtensorMap& b_lo, cudaStream_t st, int sm_count,
+                     uint8_t* sk_area = nullptr) {
+  GemmParams p = op.p;
   const int tiles_m = p.batches * ((p.rows_per_batch + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M));
   const int tiles = tiles_m * (p.N / GEMM_BLOCK_N);
   const int clusters = std::min(tiles, sm_count / 2);
   if (clusters <= 0) return SYL_OK;
-  launch_pdl(gemm3_tc_kernel, dim3(2 * clusters), dim3(GEMM3_THREADS), GEMM2_SMEM_TOTAL, st, op.a_hi, op.a_lo, b_hi, b_lo, op.o3_f32,
-             op.o3_hi, op.o3_lo, p);
+  if (sk_area && gemm_streamk_wanted(tiles, clusters, sm_count)) {
+    p.sk_ticket = reinterpret_cast<unsigned*>(sk_area);
+    p.sk_flags = reinterpret_cast<unsigned*>(sk_area + 256);
+    p.sk_partial = reinterpret_cast<float*>(sk_area + kSkHeaderBytes);
+    launch_pdl(gemm3_tc_kernel<true>, dim3(2 * clusters), dim3(GEMM3_THREADS), GEMM2_SMEM_TOTAL, st, op.a_hi, op.a_lo, b_hi, b_lo,
+               op.o3_f32, op.o3_hi, op.o3_lo, p);
+  } else {
+    launch_pdl(gemm3_tc_kernel<false>, dim3(2 * clusters), dim3(GEMM3_THREADS), GEMM2_SMEM_TOTAL, st, op.a_hi, op.a_lo, b_hi, b_lo,
+               op.o3_f32, op.o3_hi, op.o3_lo, p);
+  }
   return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
 }
 
 int launch_gemm(syl_handle* h, const GemmOp& op, cudaStream_t st, int sm_count) {
-  if (launch_gemm3_raw(op, op.w->map2_hi, op.w->map2_lo, st, sm_count) != SYL_OK)
+  // the scratch area belongs to the plan in use: forwards on different streams never share a plan
+  uint8_t* sk = h->sk_pool ? h->sk_pool + (size_t)h->plan_cur * h->sk_area : nullptr;
+  if (launch_gemm3_raw(op, op.w->map2_hi, op.w->map2_lo, st, sm_count, sk) != SYL_OK)
     return fail(h, SYL_E_CUDA, "gemm launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   return SYL_OK;
 }
@@ -586,7 +631,8 @@ int launch_posconv(syl_handle* h, const PosOp& op, cudaStream_t st, int sm_count
 bool g_attrs_set = false;
 int ensure_attrs(syl_handle* h) {
   if (g_attrs_set) return SYL_OK;
-  CUDA_TRY(h, cudaFuncSetAttribute(gemm3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL));
+  CUDA_TRY(h, cudaFuncSetAttribute(gemm3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL));
+  CUDA_TRY(h, cudaFuncSetAttribute(gemm3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL));
   CUDA_TRY(h, cudaFuncSetAttribute(posconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM_TOTAL));
   CUDA_TRY(h, cudaFuncSetAttribute(posconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM_TOTAL));
   CUDA_TRY(h, (cudaFuncSetAttribute(attention7_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL)));
@@ -968,6 +1014,12 @@ int syl_finalize(syl_handle* h) {
   CUDA_TRY(h, cudaSetDevice(h->device));
   int rc = ensure_attrs(h);
   if (rc) return rc;
+  if (streamk_enabled() && !h->sk_pool) {
+    h->sk_area = streamk_area_bytes(h->sm_count);
+    const size_t bytes = h->sk_area * syl_handle::kPlans;
+    if (!(h->sk_pool = dev_alloc<uint8_t>(h, bytes))) return fail(h, SYL_E_CUDA, "cudaMalloc of the stream-K scratch pool failed");
+    CUDA_TRY(h, cudaMemset(h->sk_pool, 0, bytes));   // tickets and flags start at zero and return to zero after every launch
+  }
   const std::string fe = "feature_extractor.conv_layers.";
   if (!(h->conv0_w = copy_vec(h, fe + "0.conv.weight", (size_t)kC * 10))) return SYL_E_STATE;
   if (!(h->conv0_bfrag = dev_alloc<uint4>(h, 64 * 32))) return fail(h, SYL_E_CUDA, "cudaMalloc failed");
@@ -1366,7 +1418,7 @@ int syl_gemm_f32(const float* A, const float* W, const float* bias, const float*
   CUtensorMap b2_hi, b2_lo;     // this CTA's half of the B tile
   if (!make_tmap_f16(&b2_hi, w_hi, 2, wd, wsd, 128, &err) || !make_tmap_f16(&b2_lo, w_lo, 2, wd, wsd, 128, &err))
     return fail(nullptr, SYL_E_CUDA, "%s", err.c_str());
-  if (cudaFuncSetAttribute(gemm3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL) != cudaSuccess)
+  if (cudaFuncSetAttribute(gemm3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL) != cudaSuccess)
     return fail(nullptr, SYL_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (launch_gemm3_raw(op, b2_hi, b2_lo, st, sms) != SYL_OK)
     return fail(nullptr, SYL_E_CUDA, "gemm launch failed: %s", cudaGetErrorString(cudaGetLastError()));
