@@ -543,6 +543,18 @@ bool make_o_maps(syl_handle* h, GemmOp& op, float* f32, __half* hi, __half* lo, 
   return true;
 }
 
+// Residual add in the out-projection / FFN2 epilogue instead of the LayerNorm (gemm3_tc.cuh, kRes).  Off by default:
+// written at the end of round 1 after the GPU budget was spent.  SYL_RESID_EPI=1: FFN2 only (K = 3072, its epilogue
+// has slack); 2: the out-projection as well.
+int resid_epilogue_level() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SYL_RESID_EPI");
+    v = e ? std::max(0, atoi(e)) : 0;
+  }
+  return v;
+}
+
 // Stream-K schedule of the GEMM (gemm3_tc.cuh).  Off by default: written at the end of round 1 after the GPU budget
 // was spent, never run on a GPU yet.  SYL_STREAMK=1 allocates the scratch pool at finalize and uses the schedule for
 // GEMMs whose last round of whole tiles leaves at least SYL_STREAMK_PCT percent (default 4) of the cluster slots idle.
@@ -582,16 +594,22 @@ int launch_gemm3_raw(const GemmOp& op, const CUtensorMap& b_hi, const CUtensorMa
   const int tiles = tiles_m * (p.N / GEMM_BLOCK_N);
   const int clusters = std::min(tiles, sm_count / 2);
   if (clusters <= 0) return SYL_OK;
-  if (sk_area && gemm_streamk_wanted(tiles, clusters, sm_count)) {
+  const bool sk = sk_area && gemm_streamk_wanted(tiles, clusters, sm_count);
+  if (sk) {
     p.sk_ticket = reinterpret_cast<unsigned*>(sk_area);
     p.sk_flags = reinterpret_cast<unsigned*>(sk_area + 256);
     p.sk_partial = reinterpret_cast<float*>(sk_area + kSkHeaderBytes);
-    launch_pdl(gemm3_tc_kernel<true>, dim3(2 * clusters), dim3(GEMM3_THREADS), GEMM2_SMEM_TOTAL, st, op.a_hi, op.a_lo, b_hi, b_lo,
-               op.o3_f32, op.o3_hi, op.o3_lo, p);
-  } else {
-    launch_pdl(gemm3_tc_kernel<false>, dim3(2 * clusters), dim3(GEMM3_THREADS), GEMM2_SMEM_TOTAL, st, op.a_hi, op.a_lo, b_hi, b_lo,
-               op.o3_f32, op.o3_hi, op.o3_lo, p);
   }
+  const dim3 grid(2 * clusters), block(GEMM3_THREADS);
+#define SYL_LAUNCH_GEMM3(SK, RES)                                                                                           \
+  launch_pdl(gemm3_tc_kernel<SK, RES>, grid, block, GEMM2_SMEM_TOTAL, st, op.a_hi, op.a_lo, b_hi, b_lo, op.o3_f32, op.o3_hi, \
+             op.o3_lo, p)
+  if (p.res_hi) {
+    if (sk) SYL_LAUNCH_GEMM3(true, true); else SYL_LAUNCH_GEMM3(false, true);
+  } else {
+    if (sk) SYL_LAUNCH_GEMM3(true, false); else SYL_LAUNCH_GEMM3(false, false);
+  }
+#undef SYL_LAUNCH_GEMM3
   return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
 }
 
@@ -631,8 +649,10 @@ int launch_posconv(syl_handle* h, const PosOp& op, cudaStream_t st, int sm_count
 bool g_attrs_set = false;
 int ensure_attrs(syl_handle* h) {
   if (g_attrs_set) return SYL_OK;
-  CUDA_TRY(h, cudaFuncSetAttribute(gemm3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL));
-  CUDA_TRY(h, cudaFuncSetAttribute(gemm3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL));
+  CUDA_TRY(h, (cudaFuncSetAttribute(gemm3_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL)));
+  CUDA_TRY(h, (cudaFuncSetAttribute(gemm3_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL)));
+  CUDA_TRY(h, (cudaFuncSetAttribute(gemm3_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL)));
+  CUDA_TRY(h, (cudaFuncSetAttribute(gemm3_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL)));
   CUDA_TRY(h, cudaFuncSetAttribute(posconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM_TOTAL));
   CUDA_TRY(h, cudaFuncSetAttribute(posconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM_TOTAL));
   CUDA_TRY(h, (cudaFuncSetAttribute(attention7_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL)));
@@ -760,6 +780,11 @@ int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
       op.p.N = kH;
       op.p.n_pass = split_enc ? 3 : 1;
       op.p.bias = w.out.bias;
+      if (resid_epilogue_level() >= 2) {
+        op.p.res_hi = at<__half>(ws, L.h16_hi);
+        op.p.res_lo = at<__half>(ws, L.h16_lo);
+        op.p.res_ld = kH;
+      }
       if (!make_o_maps(h, op, at<float>(ws, L.pre), nullptr, nullptr, kH)) return SYL_E_CUDA;
     }
     {
@@ -781,6 +806,11 @@ int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
       op.p.N = kH;
       op.p.n_pass = split_enc ? 3 : 1;
       op.p.bias = w.ffn2.bias;
+      if (resid_epilogue_level() >= 1) {
+        op.p.res_hi = at<__half>(ws, L.h16_hi);
+        op.p.res_lo = at<__half>(ws, L.h16_lo);
+        op.p.res_ld = kH;
+      }
       if (!make_o_maps(h, op, at<float>(ws, L.pre), nullptr, nullptr, kH)) return SYL_E_CUDA;
     }
   }
@@ -900,8 +930,9 @@ int run_layer(syl_handle* h, int l, float* h_out, cudaStream_t st) {
   }
   {
     StageTimer tm(h, ST_LN, st);   // h = LN(h + attn); the residual stream is the fp16 pair (h16_hi, h16_lo), in place
-    launch_ln<kH>(at<float>(ws, L.pre), nullptr, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), w.ln1_g, w.ln1_b, M, nullptr,
-                  at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), st);
+    const bool fused = pl.out[l].p.res_hi != nullptr;   // the out-projection epilogue already added the residual
+    launch_ln<kH>(at<float>(ws, L.pre), nullptr, fused ? nullptr : at<__half>(ws, L.h16_hi), fused ? nullptr : at<__half>(ws, L.h16_lo),
+                  w.ln1_g, w.ln1_b, M, nullptr, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), st);
   }
   {
     StageTimer tm(h, ST_FFN1, st);
@@ -913,8 +944,9 @@ int run_layer(syl_handle* h, int l, float* h_out, cudaStream_t st) {
   }
   {
     StageTimer tm(h, ST_LN, st);   // h = LN(h + ffn); fp32 only where the caller wants the layer output (h_out)
-    launch_ln<kH>(at<float>(ws, L.pre), nullptr, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), w.ln2_g, w.ln2_b, M, h_out,
-                  at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), st);
+    const bool fused = pl.ffn2[l].p.res_hi != nullptr;
+    launch_ln<kH>(at<float>(ws, L.pre), nullptr, fused ? nullptr : at<__half>(ws, L.h16_hi), fused ? nullptr : at<__half>(ws, L.h16_lo),
+                  w.ln2_g, w.ln2_b, M, h_out, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), st);
   }
   CUDA_TRY(h, cudaGetLastError());
   return SYL_OK;
@@ -1418,7 +1450,7 @@ int syl_gemm_f32(const float* A, const float* W, const float* bias, const float*
   CUtensorMap b2_hi, b2_lo;     // this CTA's half of the B tile
   if (!make_tmap_f16(&b2_hi, w_hi, 2, wd, wsd, 128, &err) || !make_tmap_f16(&b2_lo, w_lo, 2, wd, wsd, 128, &err))
     return fail(nullptr, SYL_E_CUDA, "%s", err.c_str());
-  if (cudaFuncSetAttribute(gemm3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL) != cudaSuccess)
+  if (cudaFuncSetAttribute(gemm3_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL) != cudaSuccess)
     return fail(nullptr, SYL_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (launch_gemm3_raw(op, b2_hi, b2_lo, st, sms) != SYL_OK)
     return fail(nullptr, SYL_E_CUDA, "gemm launch failed: %s", cudaGetErrorString(cudaGetLastError()));

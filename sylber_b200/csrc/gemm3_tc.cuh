@@ -54,7 +54,11 @@ __device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <bool kSK>
+// kRes: the epilogue adds a residual given as an fp16 pair (hi + lo, the encoder's residual stream) to acc + bias, so
+// the LayerNorm after the out-projection / FFN2 reads one tensor instead of two (same 12 bytes per element in total,
+// but 4 of them move into a kernel that is not HBM bound).  The sum is formed exactly as the LayerNorm forms it,
+// (acc + bias) + (hi + lo), so results are bit-identical to the unfused path.  Off by default (SYL_RESID_EPI).
+template <bool kSK, bool kRes>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM3_THREADS, 1)
 gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__ CUtensorMap a_lo,
                const __grid_constant__ CUtensorMap b_hi, const __grid_constant__ CUtensorMap b_lo,
@@ -335,6 +339,25 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
         if (p.act == 1) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) gelu_fast2(v[2 * i], v[2 * i + 1], v[2 * i], v[2 * i + 1]);
+        }
+        if constexpr (kRes) {
+          if (row_in_batch < p.rows_per_batch) {     // rows beyond the matrix are clipped by the TMA store, not by these loads
+            const size_t off = ((size_t)batch * p.rows_per_batch + row_in_batch) * p.res_ld + col0;
+            const uint4* hp = reinterpret_cast<const uint4*>(p.res_hi + off);
+            const uint4* lp = reinterpret_cast<const uint4*>(p.res_lo + off);
+            const uint4 hq[2] = {hp[0], hp[1]}, lq[2] = {lp[0], lp[1]};
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const uint32_t hw[4] = {hq[i].x, hq[i].y, hq[i].z, hq[i].w}, lw[4] = {lq[i].x, lq[i].y, lq[i].z, lq[i].w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
+                const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[j]));
+                v[8 * i + 2 * j] += hf.x + lf.x;
+                v[8 * i + 2 * j + 1] += hf.y + lf.y;
+              }
+            }
+          }
         }
         if (zero_row) {
 #pragma unroll

@@ -125,7 +125,7 @@ def _streamk_items(cluster, clusters, tiles, kb_total):
     return items
 
 
-@pytest.mark.parametrize("tiles,kb_total", [(192, 12), (192, 48), (192, 8), (768, 12), (256, 48), (128, 48), (576, 12),
+@pytest.mark.parametrize("tiles,kb_total", [(189, 12), (189, 48), (192, 8), (768, 12), (256, 48), (128, 48), (576, 12),
                                             (75, 1), (147, 3), (4032, 24), (1000, 7)])
 def test_streamk_schedule_invariants(tiles, kb_total):
     """What the kernel's fix-up protocol relies on, checked on the schedule arithmetic for the GEMM shapes of the
