@@ -347,6 +347,19 @@ int fail(syl_handle* h, int code, const char* fmt, ...) {
   return code;
 }
 
+// Launch checks read cudaGetLastError(), which also returns whatever error ANOTHER user of the CUDA runtime on this thread
+// left behind (PyTorch, a profiler, a query that answered "not ready"): a stale error would be blamed on our launch and
+// fail a call that did nothing wrong.  Every entry point that launches therefore drops a pending non-sticky error first
+// (SYL_ENTER); a sticky one - a device fault - is returned by every later runtime call anyway and still surfaces.
+// launch_ok() keeps the error it consumed so that the message can name it.
+#define SYL_ENTER() (void)cudaGetLastError()
+thread_local cudaError_t g_launch_err = cudaSuccess;
+inline bool launch_ok() {
+  g_launch_err = cudaGetLastError();
+  return g_launch_err == cudaSuccess;
+}
+inline const char* launch_err() { return cudaGetErrorString(g_launch_err); }
+
 cudaEvent_t prof_event(syl_handle* h) {
   if (h->pool_used == h->pool.size()) {
     cudaEvent_t e;
@@ -610,14 +623,14 @@ int launch_gemm3_raw(const GemmOp& op, const CUtensorMap& b_hi, const CUtensorMa
     if (sk) SYL_LAUNCH_GEMM3(true, false); else SYL_LAUNCH_GEMM3(false, false);
   }
 #undef SYL_LAUNCH_GEMM3
-  return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
+  return launch_ok() ? SYL_OK : SYL_E_CUDA;
 }
 
 int launch_gemm(syl_handle* h, const GemmOp& op, cudaStream_t st, int sm_count) {
   // the scratch area belongs to the plan in use: forwards on different streams never share a plan
   uint8_t* sk = h->sk_pool ? h->sk_pool + (size_t)h->plan_cur * h->sk_area : nullptr;
   if (launch_gemm3_raw(op, op.w->map2_hi, op.w->map2_lo, st, sm_count, sk) != SYL_OK)
-    return fail(h, SYL_E_CUDA, "gemm launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail(h, SYL_E_CUDA, "gemm launch failed: %s", launch_err());
   return SYL_OK;
 }
 
@@ -869,7 +882,7 @@ int launch_attention(const CUtensorMap& qkv, const CUtensorMap& o_hi, const CUte
     launch_pdl(attention7_kernel<1, false>, dim3(grid), dim3(ATT7_THREADS), ATT7_SMEM_TOTAL, st, qkv, o_hi, o_lo, ap);
   else
     launch_pdl(attention7_kernel<0, false>, dim3(grid), dim3(ATT7_THREADS), ATT7_SMEM_TOTAL, st, qkv, o_hi, o_lo, ap);
-  return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
+  return launch_ok() ? SYL_OK : SYL_E_CUDA;
 }
 
 int run_frontend(syl_handle* h, const float* wav, cudaStream_t st) {
@@ -922,7 +935,7 @@ int run_layer(syl_handle* h, int l, float* h_out, cudaStream_t st) {
   {
     StageTimer tm(h, ST_ATTN, st);
     if (launch_attention(pl.attn_map, pl.ctx_hi_map, pl.ctx_lo_map, at<int32_t>(ws, L.valid), B, T, split_enc, h->sm_count, st))
-      return fail(h, SYL_E_CUDA, "attention launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return fail(h, SYL_E_CUDA, "attention launch failed: %s", launch_err());
   }
   {
     StageTimer tm(h, ST_OUT, st);
@@ -958,7 +971,7 @@ int run_segment(const float* states, int B, int T, float thr_norm, float thr_mer
   launch_pdl(frame_sqnorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, states, rows, nsq);
   launch_pdl(segment_kernel, dim3(B), dim3(32), 0, st, states, nsq, T, thr_norm, thr_merge, seg, seg_count, max_seg, scratch);
   if (seg_feat) launch_pdl(segment_pool_kernel, dim3(max_seg, B), dim3(192), 0, st, states, T, seg, seg_count, max_seg, seg_feat);
-  return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
+  return launch_ok() ? SYL_OK : SYL_E_CUDA;
 }
 
 }  // namespace
@@ -968,7 +981,7 @@ static int run_mma_probe(int iters, int ctas, long long* out_dev, cudaStream_t s
   if (cudaFuncSetAttribute(mma_probe_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 1024 + 64) != cudaSuccess)
     return SYL_E_CUDA;
   mma_probe_kernel<N><<<ctas, 128, 65536 + 1024 + 64, st>>>(iters, out_dev);
-  return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
+  return launch_ok() ? SYL_OK : SYL_E_CUDA;
 }
 
 // ================================================================================================
@@ -1015,6 +1028,7 @@ void syl_destroy(syl_handle* h) {
   for (cudaEvent_t e : h->pool) cudaEventDestroy(e);
   for (Plan& pl : h->plans)
     for (auto& g : pl.graphs) cudaGraphExecDestroy(g.exec);
+  (void)cudaGetLastError();   // teardown never leaves a pending error for the next runtime user of this thread
   delete h;
 }
 
@@ -1041,6 +1055,7 @@ int syl_load_weight(syl_handle* h, const char* name, const void* dev_ptr, const 
 }
 
 int syl_finalize(syl_handle* h) {
+  SYL_ENTER();
   if (!h) return SYL_E_ARG;
   if (h->finalized) return SYL_OK;
   CUDA_TRY(h, cudaSetDevice(h->device));
@@ -1183,7 +1198,7 @@ static int enqueue_forward(syl_handle* h, Plan& pl, const float* wav, const int3
     StageTimer tm(h, ST_SEG, st);
     rc = run_segment(hidden, batch, T, thr_norm, thr_merge, seg, seg_count, seg_feat, max_seg,
                      at<float>(workspace, L.nsq), at<int32_t>(workspace, L.seg_scratch), st);
-    if (rc) return fail(h, rc, "segmentation launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc) return fail(h, rc, "segmentation launch failed: %s", launch_err());
   }
   return SYL_OK;
 }
@@ -1191,6 +1206,7 @@ static int enqueue_forward(syl_handle* h, Plan& pl, const float* wav, const int3
 int syl_forward(syl_handle* h, const float* wav, const int32_t* n_samples, int batch, int t_samp_max, float* hidden,
                 int32_t* seg, int32_t* seg_count, float* seg_feat, int max_seg, float thr_norm, float thr_merge,
                 void* workspace, size_t workspace_bytes, void* stream) {
+  SYL_ENTER();
   if (!h) return SYL_E_ARG;
   if (!h->finalized) return fail(h, SYL_E_STATE, "syl_forward before syl_finalize");
   if (!wav || !hidden || !workspace || batch <= 0) return fail(h, SYL_E_ARG, "syl_forward: null pointer or empty batch");
@@ -1260,6 +1276,7 @@ int syl_set_graph_mode(syl_handle* h, int on) {
 
 int syl_conv_frontend(syl_handle* h, const float* wav, int batch, int t_samp_max, float* feats, void* workspace,
                       size_t workspace_bytes, void* stream) {
+  SYL_ENTER();
   if (!h) return SYL_E_ARG;
   if (!h->finalized) return fail(h, SYL_E_STATE, "syl_conv_frontend before syl_finalize");
   if (!wav || !feats || !workspace || batch <= 0 || t_samp_max < 400) return fail(h, SYL_E_ARG, "syl_conv_frontend: bad arguments");
@@ -1278,6 +1295,7 @@ int syl_conv_frontend(syl_handle* h, const float* wav, int batch, int t_samp_max
 
 int syl_encoder_layer(syl_handle* h, int layer, const float* h_in, const int32_t* valid_frames, int batch, int T,
                       float* h_out, void* workspace, size_t workspace_bytes, void* stream) {
+  SYL_ENTER();
   if (!h) return SYL_E_ARG;
   if (!h->finalized) return fail(h, SYL_E_STATE, "syl_encoder_layer before syl_finalize");
   if (!h_in || !h_out || !workspace || batch <= 0 || T <= 0 || layer < 0 || layer >= h->n_layers)
@@ -1303,6 +1321,7 @@ int syl_encoder_layer(syl_handle* h, int layer, const float* h_in, const int32_t
 }
 
 int syl_attention(const void* qkv_f16, const int32_t* kv_len, int batch, int T, void* out_f16, void* stream) {
+  SYL_ENTER();
   std::string err;
   if (!qkv_f16 || !out_f16 || batch <= 0 || T <= 0) return fail(nullptr, SYL_E_ARG, "syl_attention: bad arguments");
   if (cudaFuncSetAttribute(attention7_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL) != cudaSuccess ||
@@ -1320,7 +1339,7 @@ int syl_attention(const void* qkv_f16, const int32_t* kv_len, int batch, int T, 
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (launch_attention(map, omap, omap, kv_len, batch, T, 0, sms, reinterpret_cast<cudaStream_t>(stream)) != SYL_OK)
-    return fail(nullptr, SYL_E_CUDA, "attention launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail(nullptr, SYL_E_CUDA, "attention launch failed: %s", launch_err());
   return SYL_OK;
 }
 
@@ -1342,6 +1361,7 @@ size_t syl_pcm16_workspace_bytes(int batch, int t_samp_max) {
 
 int syl_prepare_pcm16(const int16_t* pcm, const int64_t* offsets, const int32_t* n_samples, int batch, int t_samp_max,
                       int normalize, float* wav_out, void* workspace, size_t workspace_bytes, void* stream) {
+  SYL_ENTER();
   if (!pcm || !offsets || !n_samples || !wav_out || !workspace || batch <= 0 || t_samp_max <= 0)
     return fail(nullptr, SYL_E_ARG, "syl_prepare_pcm16: bad arguments");
   if (workspace_bytes < syl_pcm16_workspace_bytes(batch, t_samp_max))
@@ -1351,11 +1371,12 @@ int syl_prepare_pcm16(const int16_t* pcm, const int64_t* offsets, const int32_t*
   double* part = reinterpret_cast<double*>(workspace);
   if (normalize) pcm16_stats_kernel<int16_t><<<dim3(chunks, batch), PCM_THREADS, 0, st>>>(pcm, offsets, n_samples, chunks, part);
   pcm16_apply_kernel<int16_t><<<dim3(chunks, batch), PCM_THREADS, 0, st>>>(pcm, offsets, n_samples, chunks, part, normalize, t_samp_max, wav_out);
-  return cudaGetLastError() == cudaSuccess ? SYL_OK : fail(nullptr, SYL_E_CUDA, "syl_prepare_pcm16 launch failed");
+  return launch_ok() ? SYL_OK : fail(nullptr, SYL_E_CUDA, "syl_prepare_pcm16 launch failed: %s", launch_err());
 }
 
 int syl_prepare_f32(const float* wav, const int64_t* offsets, const int32_t* n_samples, int batch, int t_samp_max,
                     int normalize, float* wav_out, void* workspace, size_t workspace_bytes, void* stream) {
+  SYL_ENTER();
   if (!wav || !offsets || !n_samples || !wav_out || !workspace || batch <= 0 || t_samp_max <= 0)
     return fail(nullptr, SYL_E_ARG, "syl_prepare_f32: bad arguments");
   if (workspace_bytes < syl_pcm16_workspace_bytes(batch, t_samp_max))
@@ -1365,25 +1386,27 @@ int syl_prepare_f32(const float* wav, const int64_t* offsets, const int32_t* n_s
   double* part = reinterpret_cast<double*>(workspace);
   if (normalize) pcm16_stats_kernel<float><<<dim3(chunks, batch), PCM_THREADS, 0, st>>>(wav, offsets, n_samples, chunks, part);
   pcm16_apply_kernel<float><<<dim3(chunks, batch), PCM_THREADS, 0, st>>>(wav, offsets, n_samples, chunks, part, normalize, t_samp_max, wav_out);
-  return cudaGetLastError() == cudaSuccess ? SYL_OK : fail(nullptr, SYL_E_CUDA, "syl_prepare_f32 launch failed");
+  return launch_ok() ? SYL_OK : fail(nullptr, SYL_E_CUDA, "syl_prepare_f32 launch failed: %s", launch_err());
 }
 
 int syl_resample(const float* wav_in, const int32_t* n_in, int batch, int t_in_max, const float* kernel, int orig_g, int new_g,
                  int width, float* wav_out, int32_t* n_out, int t_out_max, void* stream) {
+  SYL_ENTER();
   if (!wav_in || !n_in || !kernel || !wav_out || batch <= 0 || t_in_max <= 0 || t_out_max <= 0 || orig_g <= 0 || new_g <= 0 || width < 0)
     return fail(nullptr, SYL_E_ARG, "syl_resample: bad arguments");
   resample_kernel<<<dim3((t_out_max + 255) / 256, batch), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       wav_in, n_in, t_in_max, kernel, orig_g, new_g, width, wav_out, n_out, t_out_max);
-  return cudaGetLastError() == cudaSuccess ? SYL_OK : fail(nullptr, SYL_E_CUDA, "syl_resample launch failed");
+  return launch_ok() ? SYL_OK : fail(nullptr, SYL_E_CUDA, "syl_resample launch failed: %s", launch_err());
 }
 
 int syl_kmeans_assign(const float* feats, int n, const float* centroids, int K, int normalize, int32_t* idx_out,
                       float* dist_out, void* stream) {
+  SYL_ENTER();
   if (n == 0) return SYL_OK;
   if (!feats || !centroids || !idx_out || n < 0 || K <= 0) return fail(nullptr, SYL_E_ARG, "syl_kmeans_assign: bad arguments");
   kmeans_assign_kernel<<<(n + KM_ROWS - 1) / KM_ROWS, KM_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       feats, n, centroids, K, normalize, idx_out, dist_out);
-  return cudaGetLastError() == cudaSuccess ? SYL_OK : fail(nullptr, SYL_E_CUDA, "syl_kmeans_assign launch failed");
+  return launch_ok() ? SYL_OK : fail(nullptr, SYL_E_CUDA, "syl_kmeans_assign launch failed: %s", launch_err());
 }
 
 size_t syl_segment_workspace_bytes(int batch, int T) {
@@ -1394,6 +1417,7 @@ size_t syl_segment_workspace_bytes(int batch, int T) {
 int syl_segment(const float* states, int batch, int T, float thr_norm, float thr_merge, int32_t* seg,
                 int32_t* seg_count, float* seg_feat, int max_seg, void* workspace, size_t workspace_bytes,
                 void* stream) {
+  SYL_ENTER();
   if (!states || !seg || !seg_count || !workspace || batch <= 0 || T <= 0 || max_seg <= 0) return SYL_E_ARG;
   if (workspace_bytes < syl_segment_workspace_bytes(batch, T)) return SYL_E_WORKSPACE;
   float* nsq = reinterpret_cast<float*>(workspace);
@@ -1410,6 +1434,7 @@ size_t syl_gemm_workspace_bytes(int M, int N, int K) {
 
 int syl_gemm_f32(const float* A, const float* W, const float* bias, const float* residual, float* out, int M, int N,
                  int K, int n_pass, int act, void* workspace, size_t workspace_bytes, void* stream) {
+  SYL_ENTER();
   if (!A || !W || !out || !workspace || M <= 0 || N <= 0 || K <= 0) return fail(nullptr, SYL_E_ARG, "syl_gemm_f32: bad arguments");
   if (N % 256 != 0 || K % 64 != 0) return fail(nullptr, SYL_E_ARG, "syl_gemm_f32: N must be a multiple of 256 and K of 64");
   if (n_pass != 1 && n_pass != 3) return fail(nullptr, SYL_E_ARG, "syl_gemm_f32: n_pass must be 1 or 3");
@@ -1453,12 +1478,13 @@ int syl_gemm_f32(const float* A, const float* W, const float* bias, const float*
   if (cudaFuncSetAttribute(gemm3_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL) != cudaSuccess)
     return fail(nullptr, SYL_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (launch_gemm3_raw(op, b2_hi, b2_lo, st, sms) != SYL_OK)
-    return fail(nullptr, SYL_E_CUDA, "gemm launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail(nullptr, SYL_E_CUDA, "gemm launch failed: %s", launch_err());
   if (residual) add_inplace_kernel<<<grid_for((size_t)M * N), 256, 0, st>>>(out, residual, (size_t)M * N);
-  return cudaGetLastError() == cudaSuccess ? SYL_OK : fail(nullptr, SYL_E_CUDA, "launch failed");
+  return launch_ok() ? SYL_OK : fail(nullptr, SYL_E_CUDA, "launch failed: %s", launch_err());
 }
 
 int syl_mma_probe(int n, int iters, int ctas, void* cycles_out_dev, void* stream) {
+  SYL_ENTER();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   long long* out = reinterpret_cast<long long*>(cycles_out_dev);
   switch (n) {
@@ -1474,9 +1500,10 @@ int syl_mma_probe(int n, int iters, int ctas, void* cycles_out_dev, void* stream
 }
 
 int syl_powf_half(const float* x, float* y, int64_t n, void* stream) {
+  SYL_ENTER();
   if (!x || !y || n <= 0) return SYL_E_ARG;
   powf_half_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, n);
-  return cudaGetLastError() == cudaSuccess ? SYL_OK : SYL_E_CUDA;
+  return launch_ok() ? SYL_OK : SYL_E_CUDA;
 }
 
 int syl_num_stages(void) { return ST_COUNT; }
@@ -1508,6 +1535,7 @@ int syl_profile_read(syl_handle* h, float* ms, int* counts) {
 }
 
 int syl_read_stage(syl_handle* h, const char* name, float* out, size_t n_floats, void* stream) {
+  SYL_ENTER();
   if (!h || !name || !out) return SYL_E_ARG;
   if (!h->plans[h->plan_cur].valid) return fail(h, SYL_E_STATE, "syl_read_stage: no forward has run yet");
   const Plan& pl = h->plans[h->plan_cur];
