@@ -1477,7 +1477,22 @@ int syl_gemm_f32(const float* A, const float* W, const float* bias, const float*
     return fail(nullptr, SYL_E_CUDA, "%s", err.c_str());
   if (cudaFuncSetAttribute(gemm3_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL) != cudaSuccess)
     return fail(nullptr, SYL_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
-  if (launch_gemm3_raw(op, b2_hi, b2_lo, st, sms) != SYL_OK)
+  uint8_t* sk = nullptr;
+  if (streamk_enabled()) {
+    // test hook for the stream-K schedule: one process-wide scratch area (calls through this entry point are not concurrent)
+    static uint8_t* area = nullptr;
+    if (!area) {
+      const size_t bytes = streamk_area_bytes(sms);
+      if (cudaMalloc(&area, bytes) != cudaSuccess || cudaMemset(area, 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+        area = nullptr;
+        return fail(nullptr, SYL_E_CUDA, "stream-K scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+      }
+    }
+    sk = area;
+    if (cudaFuncSetAttribute(gemm3_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL) != cudaSuccess)
+      return fail(nullptr, SYL_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  if (launch_gemm3_raw(op, b2_hi, b2_lo, st, sms, sk) != SYL_OK)
     return fail(nullptr, SYL_E_CUDA, "gemm launch failed: %s", launch_err());
   if (residual) add_inplace_kernel<<<grid_for((size_t)M * N), 256, 0, st>>>(out, residual, (size_t)M * N);
   return launch_ok() ? SYL_OK : fail(nullptr, SYL_E_CUDA, "launch failed: %s", launch_err());
