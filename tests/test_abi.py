@@ -64,3 +64,54 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def _header_prototypes():
+    """{name: (return type, [parameter types])} parsed from the header, types reduced to a kind: 'ptr', 'int', 'float',
+    'size_t', 'int64', 'void'."""
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+
+    def kind(t):
+        t = t.strip()
+        if "*" in t:
+            return "ptr"
+        t = re.sub(r"\b(const|unsigned|signed)\b", "", t).split()
+        base = t[0] if t else "void"
+        return {"int": "int", "int32_t": "int", "float": "float", "size_t": "size_t", "int64_t": "int64", "void": "void"}[base]
+
+    src = "\n".join(l for l in src.splitlines() if not l.lstrip().startswith("#"))
+    src = src.replace('extern "C" {', "").replace("}", ";")
+    out = {}
+    for stmt in src.split(";"):
+        m = re.match(r"\s*([\w\s\*]+?)\b(syl_[a-z0-9_]+)\s*\((.*)\)\s*$", stmt, flags=re.S)
+        if not m or stmt.lstrip().startswith("typedef"):
+            continue
+        ret, name, params = m.group(1), m.group(2), m.group(3)
+        plist = []
+        if params.strip() not in ("", "void"):
+            for prm in params.split(","):
+                prm = prm.strip()
+                plist.append("ptr" if "*" in prm else kind(re.sub(r"\b\w+$", "", prm)))      # drop the parameter name
+        out[name] = (kind(ret), plist)
+    return out
+
+
+def test_ctypes_table_matches_header_prototypes():
+    """Argument count, order and kind of every binding in sylber_b200/_lib.py against include/sylber_b200.h: a swapped
+    or missing argument in a ctypes table is silent until it corrupts a call."""
+    protos = _header_prototypes()
+    assert set(protos) == set(_lib.SIGNATURES)
+
+    def ckind(t):
+        if t is None:
+            return "void"
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or isinstance(t, type(ctypes.POINTER(ctypes.c_int))) and issubclass(t, ctypes._Pointer):
+            return "ptr"
+        return {ctypes.c_int: "int", ctypes.c_float: "float", ctypes.c_size_t: "size_t", ctypes.c_int64: "int64"}[t]
+
+    for name, (ret, params) in protos.items():
+        res, args = _lib.SIGNATURES[name]
+        assert [ckind(a) for a in args] == params, (name, params, [ckind(a) for a in args])
+        assert ckind(res) == ret, (name, ret, res)
