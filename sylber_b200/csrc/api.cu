@@ -898,8 +898,15 @@ int run_frontend(syl_handle* h, const float* wav, cudaStream_t st) {
                at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift));
     __half* hi = at<__half>(ws, L.act_hi[0]);
     __half* lo = conv_split(h->mode, 1) ? at<__half>(ws, L.act_lo[0]) : nullptr;
+    static const int conv0_mb = [] {     // SYL_CONV0_MB=5: 48-register build, 5 blocks per SM (frontend.cuh)
+      const char* e = getenv("SYL_CONV0_MB");
+      return e ? atoi(e) : 4;
+    }();
     if (lo)
       launch_pdl(conv0_mma_kernel<true>, dim3((L0 + C0M_T - 1) / C0M_T, B), dim3(C0M_THREADS), 0, st, wav, pl.t_samp, L0,
+                 h->conv0_bfrag, at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift), hi, lo);
+    else if (conv0_mb == 5)
+      launch_pdl(conv0_mma_kernel<false, 5>, dim3((L0 + C0M_T - 1) / C0M_T, B), dim3(C0M_THREADS), 0, st, wav, pl.t_samp, L0,
                  h->conv0_bfrag, at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift), hi, lo);
     else
       launch_pdl(conv0_mma_kernel<false>, dim3((L0 + C0M_T - 1) / C0M_T, B), dim3(C0M_THREADS), 0, st, wav, pl.t_samp, L0,
