@@ -843,7 +843,11 @@ int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
 template <int D>
 void launch_ln(const float* x, const float* add, const __half* add_hi, const __half* add_lo, const float* g, const float* b, int rows,
                float* of, __half* ohi, __half* olo, cudaStream_t st) {
-  const int warps = 8;
+  static const int warps = [] {        // SYL_LN_WARPS=4: 128-thread blocks (A/B not run yet); the kernel is built for <= 256 threads
+    const char* e = getenv("SYL_LN_WARPS");
+    const int v = e ? atoi(e) : 8;
+    return (v == 2 || v == 4 || v == 8) ? v : 8;
+  }();
   launch_pdl(layernorm_rows_kernel<D>, dim3((rows + warps - 1) / warps), dim3(warps * 32), 0, st, x, add, add_hi, add_lo, g, b, rows, of,
              ohi, olo);
 }

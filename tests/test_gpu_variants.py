@@ -15,7 +15,7 @@ pytestmark = [pytest.mark.gpu,
 
 
 @pytest.mark.parametrize("args", [["SYL_RESID_EPI=1", "--exact"], ["SYL_RESID_EPI=2", "--exact"], ["SYL_STREAMK=1"],
-                                  ["SYL_STREAMK=1", "SYL_STREAMK_PCT=0"], ["SYL_STREAMK=1", "SYL_RESID_EPI=2"], ["SYL_CONV0_MB=5", "--exact"]])
+                                  ["SYL_STREAMK=1", "SYL_STREAMK_PCT=0"], ["SYL_STREAMK=1", "SYL_RESID_EPI=2"], ["SYL_CONV0_MB=5", "--exact"], ["SYL_LN_WARPS=4", "--exact"]])
 def test_variant_matches_default_build(cuda, args):
     p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "variant_check.py")] + args, capture_output=True, text=True,
                        timeout=800)

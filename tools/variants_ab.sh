@@ -17,6 +17,7 @@ run streamk SYL_STREAMK=1
 run resid1 SYL_RESID_EPI=1
 run resid2 SYL_RESID_EPI=2
 run conv0mb5 SYL_CONV0_MB=5
+run lnwarps4 SYL_LN_WARPS=4
 run all SYL_STREAMK=1 SYL_RESID_EPI=2 SYL_CONV0_MB=5
 run default_again
 python tools/bench_summary.py $out/bench_*.json
