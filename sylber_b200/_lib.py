@@ -83,12 +83,18 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libsylber_b200.so")
+    tmp = f"{_SO}.{os.getpid()}.tmp"       # never leave a half-written library where another process may load it
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177",
-           "-o", _SO, os.path.join(_CSRC, "api.cu")]
+           "-o", tmp, os.path.join(_CSRC, "api.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
-    subprocess.check_call(cmd, cwd=_CSRC)
+    try:
+        subprocess.check_call(cmd, cwd=_CSRC)
+        os.replace(tmp, _SO)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
     return _SO
 
 
