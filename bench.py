@@ -157,8 +157,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from sylber_b200.weights import syllabic_test_state_dict
-    sd = syllabic_test_state_dict(args.layers, 0)
+    from sylber_b200.weights import syllabic_test_state_dict, SPEECH_LIKE_BIAS_NORM
+    sd = syllabic_test_state_dict(args.layers, 0, bias_norm=SPEECH_LIKE_BIAS_NORM)
     batch = 4 if N_SAMPLES <= 160000 else 1
     fps, ms = time_cpu(sd, args.layers, batch, args.steps, args.warmup)
     line = {
@@ -183,7 +183,7 @@ def run_reference(args):
 def run_ours(args):
     import torch.distributed as dist
     from sylber_b200 import Segmenter
-    from sylber_b200.weights import syllabic_test_state_dict
+    from sylber_b200.weights import syllabic_test_state_dict, SPEECH_LIKE_BIAS_NORM
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -198,7 +198,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     layers = args.layers
-    sd = syllabic_test_state_dict(layers, 0)
+    sd = syllabic_test_state_dict(layers, 0, bias_norm=SPEECH_LIKE_BIAS_NORM)
     seg = Segmenter(model_ckpt=None, state_dict=sd, encoding_layer=layers, device=f"cuda:{local}", mode=args.mode,
                     max_batch=BATCH_PER_GPU, **({"streams": args.streams} if args.streams else {}))
     eng = seg._engine

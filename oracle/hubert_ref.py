@@ -84,9 +84,11 @@ def frame_mask(n_samples, T):
     return torch.arange(T)[None, :] < valid[:, None]
 
 
-def encoder_layer(sd, i, h, key_bias, q=None):
-    """Post-LN transformer layer (HF:388-405)."""
+def encoder_layer(sd, i, h, key_bias, q=None, q_attn=None):
+    """Post-LN transformer layer (HF:388-405).  `q` rounds the operands of the linears, `q_attn` (default: q) those of
+    Q.K^T and P.V - precision studies only."""
     q = q or (lambda t: t)
+    qa = q_attn or q
     p = f"encoder.layers.{i}."
     B, T, _ = h.shape
 
@@ -96,11 +98,11 @@ def encoder_layer(sd, i, h, key_bias, q=None):
     qh = lin(h, "attention.q_proj").view(B, T, HEADS, -1).transpose(1, 2)
     kh = lin(h, "attention.k_proj").view(B, T, HEADS, -1).transpose(1, 2)
     vh = lin(h, "attention.v_proj").view(B, T, HEADS, -1).transpose(1, 2)
-    s = torch.matmul(q(qh), q(kh).transpose(2, 3)) * (qh.shape[-1] ** -0.5)  # HF:248
+    s = torch.matmul(qa(qh), qa(kh).transpose(2, 3)) * (qh.shape[-1] ** -0.5)  # HF:248
     if key_bias is not None:
         s = s + key_bias
     pr = torch.softmax(s, dim=-1)
-    a = torch.matmul(q(pr), q(vh)).transpose(1, 2).reshape(B, T, HIDDEN)
+    a = torch.matmul(qa(pr), qa(vh)).transpose(1, 2).reshape(B, T, HIDDEN)
     a = lin(a, "attention.out_proj")
     h = F.layer_norm(h + a, (HIDDEN,), sd[p + "layer_norm.weight"], sd[p + "layer_norm.bias"], LN_EPS)
     f = F.gelu(lin(h, "feed_forward.intermediate_dense"))
@@ -110,7 +112,7 @@ def encoder_layer(sd, i, h, key_bias, q=None):
 
 
 @torch.no_grad()
-def hubert_forward(sd, wav, n_samples=None, n_layers=9, stages=None, q=None, q_conv=None):
+def hubert_forward(sd, wav, n_samples=None, n_layers=9, stages=None, q=None, q_conv=None, q_attn=None):
     """last_hidden_state of HubertModel.forward (HF:889-958) in eval mode.
 
     sd        flat fp32 state_dict with HubertModel keys
@@ -144,7 +146,7 @@ def hubert_forward(sd, wav, n_samples=None, n_layers=9, stages=None, q=None, q_c
     if stages is not None:
         stages["enc_in"] = h
     for i in range(n_layers):
-        h = encoder_layer(sd, i, h, key_bias, q)
+        h = encoder_layer(sd, i, h, key_bias, q, q_attn)
         if stages is not None:
             stages[f"layer{i}"] = h
     return h

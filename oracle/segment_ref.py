@@ -26,8 +26,9 @@ def _cos(u, v):
     return num / den_u / den_v
 
 
-def _scan(states, active, merge_thr):
-    """Phase 1 (segment_utils.py:79-108): greedy left-to-right merge of frames into runs."""
+def _scan(states, active, merge_thr, trace=None):
+    """Phase 1 (segment_utils.py:79-108): greedy left-to-right merge of frames into runs.
+    `trace` (a list) receives every threshold decision as (kind, frame, value, threshold)."""
     runs, splits = [], []
     start, centroid, count = -1, 0, 0
     for t in range(len(states)):
@@ -39,7 +40,10 @@ def _scan(states, active, merge_thr):
         if count == 0:
             centroid, count, start = states[t], 1, t
             continue
-        if _cos(centroid, states[t]) >= merge_thr:
+        sim = _cos(centroid, states[t])
+        if trace is not None:
+            trace.append(("merge", t, float(sim), float(np.float32(merge_thr))))
+        if sim >= merge_thr:
             centroid = (centroid * count + states[t]) / (count + 1)
             count += 1
         else:
@@ -53,8 +57,9 @@ def _scan(states, active, merge_thr):
     return runs, splits
 
 
-def _refine(states, runs, splits, merge_thr):
-    """Phase 2 (segment_utils.py:110-128): merge or re-place each split boundary, in order."""
+def _refine(states, runs, splits, merge_thr, trace=None):
+    """Phase 2 (segment_utils.py:110-128): merge or re-place each split boundary, in order.
+    `trace` receives ("refine_merge", cut, cos, thr) and ("refine_argmax", cut, best - runner_up, winning frame)."""
     absorbed = set()
     for cut, left in splits:
         if left >= len(runs) - 1:
@@ -63,7 +68,10 @@ def _refine(states, runs, splits, merge_thr):
         (ls, le), (rs, re) = runs[left], runs[right]
         mu_l = states[ls:le].mean(0)
         mu_r = states[rs:re].mean(0)
-        if _cos(mu_l, mu_r) >= merge_thr:
+        sim = _cos(mu_l, mu_r)
+        if trace is not None:
+            trace.append(("refine_merge", cut, float(sim), float(np.float32(merge_thr))))
+        if sim >= merge_thr:
             runs[right] = [ls, re]
             absorbed.add(left)
             continue
@@ -74,17 +82,67 @@ def _refine(states, runs, splits, merge_thr):
         to_right = _cos(window, mu_r[None, :])
         score = [to_left[:k].sum() + to_right[k:].sum() for k in range(hi - lo)]
         best = lo + int(np.argmax(score))
+        if trace is not None:
+            top = np.sort(np.asarray(score, np.float64))[::-1]
+            trace.append(("refine_argmax", cut, float(top[0] - top[1]) if len(top) > 1 else float("inf"), best))
         runs[left] = [ls, best]
         runs[right] = [best, re]
     return [r for k, r in enumerate(runs) if k not in absorbed]
 
 
-def get_segment(states, norm_thr, merge_thr, norms=None):
-    """Same contract as the reference's get_segment: (N,2) int64, or shape (0,) float64 when empty."""
+def get_segment(states, norm_thr, merge_thr, norms=None, trace=None):
+    """Same contract as the reference's get_segment: (N,2) int64, or shape (0,) float64 when empty.
+    With `trace` (a list) every threshold decision the run takes is appended in order (decision_trace below)."""
     if norms is None:
         norms = ((states ** 2).sum(-1) + _EPS) ** .5
-    runs, splits = _scan(states, norms >= norm_thr, merge_thr)
-    return np.array(_refine(states, runs, splits, merge_thr))
+    if trace is not None:
+        thr = float(np.float32(norm_thr))
+        trace.extend(("norm", t, float(v), thr) for t, v in enumerate(norms))
+    runs, splits = _scan(states, norms >= norm_thr, merge_thr, trace)
+    return np.array(_refine(states, runs, splits, merge_thr, trace))
+
+
+def decision_trace(states, norm_thr, merge_thr):
+    """(segments, decisions): every comparison get_segment makes on `states`, in execution order, as
+    (kind, frame, value, threshold) with kind in norm | merge | refine_merge (segment_utils.py:76, :96-97, :114), and
+    ("refine_argmax", cut, lead of the winning boundary over the runner-up, winning frame) for :126."""
+    trace = []
+    seg = get_segment(np.asarray(states, np.float32), norm_thr, merge_thr, trace=trace)
+    return seg, trace
+
+
+def min_margins(trace):
+    """Smallest distance to a different outcome per decision kind: |value - threshold| / threshold for norm,
+    |value - threshold| for the cosines, the winner's lead for the argmax."""
+    out = {}
+    for kind, _, v, thr in trace:
+        m = v if kind == "refine_argmax" else (abs(v - thr) / thr if kind == "norm" else abs(v - thr))
+        out[kind] = min(out.get(kind, float("inf")), m)
+    return out
+
+
+def _outcome(d):
+    return d[3] if d[0] == "refine_argmax" else d[2] >= d[3]
+
+
+def explain_difference(states_ref, states_got, norm_thr, merge_thr):
+    """Why do two state arrays of one utterance segment differently?  Replays get_segment on both and returns the
+    FIRST decision whose outcome differs: dict(kind, frame, ref, got, threshold, margin, delta).  For the threshold
+    decisions margin = |ref - threshold| and delta = |got - ref|, so a flip always has margin <= delta and what the
+    caller has to check is that delta is no larger than the per-frame state error allows.  For refine_argmax ref / got
+    are the two winners' leads, margin = the reference winner's lead, delta = the sum of both leads (how far the score
+    differences moved).  None when both runs take identical decisions."""
+    _, a = decision_trace(states_ref, norm_thr, merge_thr)
+    _, b = decision_trace(states_got, norm_thr, merge_thr)
+    for da, db in zip(a, b):
+        assert da[:2] == db[:2], (da, db)          # identical outcomes so far => identical control flow
+        if _outcome(da) != _outcome(db):
+            if da[0] == "refine_argmax":
+                return {"kind": da[0], "frame": da[1], "ref": da[2], "got": db[2], "threshold": 0.0,
+                        "margin": da[2], "delta": da[2] + db[2]}
+            return {"kind": da[0], "frame": da[1], "ref": da[2], "got": db[2], "threshold": da[3],
+                    "margin": abs(da[2] - da[3]), "delta": abs(db[2] - da[2])}
+    return None
 
 
 def package(states, segments, in_second=True):

