@@ -16,8 +16,16 @@
  *     last failure is available from syl_last_error().
  *   - work is enqueued on the CUDA stream passed in (a cudaStream_t cast to void*); the library never
  *     synchronises the device except inside syl_finalize().
- *   - one handle per device, not thread safe.  There is no CPU fallback: without an sm_100 GPU every compute
- *     entry point fails with SYL_E_CUDA.
+ *   - a handle belongs to one device; entry points that take a handle switch to that device for the duration of the
+ *     call and restore the caller's current device before returning.  Handle-less entry points (syl_segment,
+ *     syl_attention, syl_kmeans_assign, syl_prepare_*, syl_resample, syl_gemm_f32, syl_powf_half) launch on the
+ *     CURRENT device - the one their pointer arguments must live on.
+ *   - entry points that take a handle serialise on a mutex inside it (plan cache, CUDA-graph cache and profiling
+ *     records are per-handle state), so several host threads may share a handle; forwards that are in flight at the
+ *     same time must use different workspaces and output buffers.
+ *   - the library reads no environment variables.  Experiment switches and the diagnostic entry points exist only
+ *     in the -DSYL_DIAG build (libsylber_b200_diag.so).
+ *   - there is no CPU fallback: without an sm_100 GPU every compute entry point fails with SYL_E_CUDA.
  */
 #ifndef SYLBER_B200_H
 #define SYLBER_B200_H
@@ -96,10 +104,12 @@ int syl_encoder_layer(syl_handle* h, int layer, const float* h_in, const int32_t
                       float* h_out, void* workspace, size_t workspace_bytes, void* stream);
 /* attention core: qkv [batch*T, 2304] fp16 (Q pre-scaled by 1/8), out [batch*T, 768] fp16 */
 int syl_attention(const void* qkv_f16, const int32_t* kv_len, int batch, int T, void* out_f16, void* stream);
-/* diagnostic: the same launch with CTA 0 logging clock64 stamps of its MMA thread and softmax warpgroups into
+#ifdef SYL_DIAG
+/* diagnostic build only: the same launch with CTA 0 logging clock64 stamps of its MMA thread and softmax warpgroups into
  * trace_dev[7][trace_cap] (int64 device memory, zero it first); decoded by tools/attn_trace.py */
 int syl_attention_trace(const void* qkv_f16, const int32_t* kv_len, int batch, int T, void* out_f16, void* trace_dev,
                         int trace_cap, void* stream);
+#endif
 /* ---- the steps either side of the path ----
  * Front door, replaces the host preprocessing of sylber/model/sylber.py:83-87 (file branch) and :93-118 (padding):
  * pcm holds the utterances' 16 kHz int16 samples back to back on the device, utterance b = pcm[offsets[b] ..
@@ -131,9 +141,11 @@ int syl_segment(const float* states, int batch, int T, float thr_norm, float thr
 size_t syl_gemm_workspace_bytes(int M, int N, int K);
 int syl_gemm_f32(const float* A, const float* W, const float* bias, const float* residual, float* out, int M, int N,
                  int K, int n_pass, int act, void* workspace, size_t workspace_bytes, void* stream);
-/* diagnostic: cycles for `iters` x 4 back-to-back tcgen05.mma (M=128, N=n, K=16) issued by one thread of each of
+#ifdef SYL_DIAG
+/* diagnostic build only: cycles for `iters` x 4 back-to-back tcgen05.mma (M=128, N=n, K=16) issued by one thread of each of
  * `ctas` CTAs; writes the elapsed clock64 ticks of CTA 0 to cycles_out_dev (one int64) */
 int syl_mma_probe(int n, int iters, int ctas, void* cycles_out_dev, void* stream);
+#endif
 /* y[i] = powf(x[i], 0.5f) as glibc computes it (the fp64 replay used by the segmentation kernel) */
 int syl_powf_half(const float* x, float* y, int64_t n, void* stream);
 /* copy an intermediate of the most recent syl_forward / syl_conv_frontend out as fp32.

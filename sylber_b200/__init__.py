@@ -9,8 +9,9 @@ torch.distributed only.  There is no CPU fallback.
 from .segmenter import Segmenter, SpeechModel, KMeansQuantizer  # noqa: F401
 from .thresholder import Thresholder  # noqa: F401
 from .batching import plan_length_buckets  # noqa: F401
+from .distributed import segment_sharded  # noqa: F401
 from ._lib import build_library, load_library, library_path  # noqa: F401
 
-__all__ = ["Segmenter", "SpeechModel", "KMeansQuantizer", "Thresholder", "plan_length_buckets", "build_library",
+__all__ = ["Segmenter", "SpeechModel", "KMeansQuantizer", "Thresholder", "plan_length_buckets", "segment_sharded", "build_library",
            "load_library", "library_path"]
 __version__ = "0.1.0"

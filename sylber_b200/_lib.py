@@ -37,7 +37,6 @@ SIGNATURES = {
     "syl_encoder_layer": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p,
                                    _c_size_t, _c_void_p]),
     "syl_attention": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p]),
-    "syl_attention_trace": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_int, _c_void_p]),
     "syl_pcm16_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
     "syl_prepare_pcm16": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
     "syl_prepare_f32": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
@@ -50,7 +49,6 @@ SIGNATURES = {
     "syl_gemm_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
     "syl_gemm_f32": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int,
                               _c_int, _c_void_p, _c_size_t, _c_void_p]),
-    "syl_mma_probe": (_c_int, [_c_int, _c_int, _c_int, _c_void_p, _c_void_p]),
     "syl_powf_half": (_c_int, [_c_void_p, _c_void_p, ctypes.c_int64, _c_void_p]),
     "syl_read_stage": (_c_int, [_c_void_p, ctypes.c_char_p, _c_void_p, _c_size_t, _c_void_p]),
     "syl_set_active_layers": (_c_int, [_c_void_p, _c_int]),
@@ -62,7 +60,15 @@ SIGNATURES = {
     "syl_profile_read": (_c_int, [_c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
 }
 
+# entry points that exist only in the diagnostic build (-DSYL_DIAG): tools/attn_trace.py, tools/mma_probe.py
+DIAG_SIGNATURES = {
+    "syl_attention_trace": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_int, _c_void_p]),
+    "syl_mma_probe": (_c_int, [_c_int, _c_int, _c_int, _c_void_p, _c_void_p]),
+}
+_SO_DIAG = os.path.join(_PKG, "libsylber_b200_diag.so")
+
 _LIB = None
+_LIB_DIAG = None
 
 
 def library_path() -> str:
@@ -74,8 +80,11 @@ def _sources():
         os.path.join(os.path.dirname(_PKG), "include", "sylber_b200.h")]
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/api.cu for sm_100a into sylber_b200/libsylber_b200.so (in-tree so it travels to the GPU box)."""
+def build_library(force: bool = False, verbose: bool = False, diag: bool = False) -> str:
+    """Compile csrc/api.cu for sm_100a into sylber_b200/libsylber_b200.so (in-tree so it travels to the GPU box).
+    `diag=True` builds libsylber_b200_diag.so with -DSYL_DIAG instead: the SYL_* environment switches and the
+    diagnostic entry points (DIAG_SIGNATURES), which the product library does not contain."""
+    _SO = _SO_DIAG if diag else globals()["_SO"]
     if not force and os.path.exists(_SO):
         newest = max(os.path.getmtime(s) for s in _sources())
         if os.path.getmtime(_SO) >= newest:
@@ -87,6 +96,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177",
            "-o", tmp, os.path.join(_CSRC, "api.cu")]
+    if diag:
+        cmd.insert(1, "-DSYL_DIAG")
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     try:
@@ -114,6 +125,19 @@ def load_library():
         fn.argtypes = args
     _LIB = lib
     return lib
+
+
+def load_diag_library():
+    """The -DSYL_DIAG build (experiment switches from the environment + diagnostic entry points); tools only."""
+    global _LIB_DIAG
+    if _LIB_DIAG is None:
+        lib = ctypes.CDLL(build_library(diag=True))
+        for name, (res, args) in {**SIGNATURES, **DIAG_SIGNATURES}.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB_DIAG = lib
+    return _LIB_DIAG
 
 
 def check(lib, handle, rc, what):

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -21,7 +22,9 @@
 #include "gemm2_tc.cuh"
 #include "gemm3_tc.cuh"
 #include "posconv.cuh"
+#ifdef SYL_DIAG
 #include "mma_probe.cuh"
+#endif
 #include "segment.cuh"
 
 using namespace syl;
@@ -201,14 +204,20 @@ __global__ void powf_half_kernel(const float* __restrict__ x, float* __restrict_
 // device-resident step does not change beyond run-to-run noise (4.78-5.08 vs 4.86-4.94 ms), and the end-to-end path,
 // which keeps three prioritised sub-batch streams in flight, gets SLOWER (6.4 vs 5.8 ms): early-launched dependents
 // of one stream hold scheduling slots the other streams need.  Hence opt-in: SYL_PDL=1.
+// The product build reads NO environment variables: every experiment switch below exists only in the diagnostic
+// build (-DSYL_DIAG, sylber_b200/_lib.py build_library(diag=True) -> libsylber_b200_diag.so).
+#ifdef SYL_DIAG
+int diag_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SYL_PDL");
-    v = e ? atoi(e) : 0;
-  }
+  static const int v = diag_env("SYL_PDL", 0);
   return v != 0;
 }
+#else
+constexpr bool pdl_enabled() { return false; }
+#endif
 
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
@@ -296,7 +305,21 @@ struct Plan {
 
 }  // namespace
 
+// Entry points run on the handle's device and leave the caller's current device as they found it.
+struct DeviceGuard {
+  int prev = -1, dev;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int d) : dev(d) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) err = cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+};
+
 struct syl_handle {
+  std::mutex mu;      // plan cache, graph cache and profiling records are per-handle state: entry points serialise on it
   int device = 0;
   int n_layers = 9;
   int active_layers = -1;
@@ -320,8 +343,6 @@ struct syl_handle {
   int plan_cur = 0;
   uint64_t plan_clock = 0;
   int sm_count = 148;
-  uint8_t* sk_pool = nullptr;   // stream-K scratch (gemm3_tc.cuh), one area per plan; null unless SYL_STREAMK=1
-  size_t sk_area = 0;
   bool profile = false;
   bool use_graphs = true;
   std::vector<ProfRec> recs;
@@ -556,93 +577,32 @@ bool make_o_maps(syl_handle* h, GemmOp& op, float* f32, __half* hi, __half* lo, 
   return true;
 }
 
-// Residual add in the out-projection / FFN2 epilogue instead of the LayerNorm (gemm3_tc.cuh, kRes).  Off by default:
-// written at the end of round 1 after the GPU budget was spent.  SYL_RESID_EPI=1: FFN2 only (K = 3072, its epilogue
-// has slack); 2: the out-projection as well.
-int resid_epilogue_level() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SYL_RESID_EPI");
-    v = e ? std::max(0, atoi(e)) : 0;
-  }
-  return v;
-}
-
-// Stream-K schedule of the GEMM (gemm3_tc.cuh).  Off by default: written at the end of round 1 after the GPU budget
-// was spent, never run on a GPU yet.  SYL_STREAMK=1 allocates the scratch pool at finalize and uses the schedule for
-// GEMMs whose last round of whole tiles leaves at least SYL_STREAMK_PCT percent (default 4) of the cluster slots idle.
-bool streamk_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SYL_STREAMK");
-    v = (e && atoi(e) != 0) ? 1 : 0;
-  }
-  return v == 1;
-}
-int streamk_min_idle_pct() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SYL_STREAMK_PCT");
-    v = e ? std::max(0, atoi(e)) : 4;
-  }
-  return v;
-}
-constexpr size_t kSkHeaderBytes = 16384;   // ticket at byte 0, flags from byte 256 (74 clusters x 32 flags x 4 B)
-size_t streamk_area_bytes(int sm_count) { return kSkHeaderBytes + (size_t)(sm_count / 2) * GEMM3_SK_SLOT_FLOATS * sizeof(float); }
-// does the stream-K schedule apply?  Needs every cluster's share to be at least one tile (so no item is cut on both
-// sides) and all clusters of the persistent grid; pays when the last data-parallel round is badly filled.
-bool gemm_streamk_wanted(int tiles, int clusters, int sm_count) {
-  if (!streamk_enabled() || pdl_enabled()) return false;
-  if (clusters != sm_count / 2 || tiles <= clusters) return false;
-  if ((size_t)clusters * GEMM3_SK_FLAGS_PER_CLUSTER * sizeof(unsigned) + 256 > kSkHeaderBytes) return false;
-  const int rounds = (tiles + clusters - 1) / clusters;
-  const int idle = rounds * clusters - tiles;
-  return idle * 100 >= streamk_min_idle_pct() * rounds * clusters;
-}
-
-int launch_gemm3_raw(const GemmOp& op, const CUtensorMap& b_hi, const CUtensorMap& b_lo, cudaStream_t st, int sm_count,
-                     uint8_t* sk_area = nullptr) {
-  GemmParams p = op.p;
+int launch_gemm3_raw(const GemmOp& op, const CUtensorMap& b_hi, const CUtensorMap& b_lo, cudaStream_t st, int sm_count) {
+  const GemmParams& p = op.p;
   const int tiles_m = p.batches * ((p.rows_per_batch + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M));
   const int tiles = tiles_m * (p.N / GEMM_BLOCK_N);
   const int clusters = std::min(tiles, sm_count / 2);
   if (clusters <= 0) return SYL_OK;
-  const bool sk = sk_area && gemm_streamk_wanted(tiles, clusters, sm_count);
-  if (sk) {
-    p.sk_ticket = reinterpret_cast<unsigned*>(sk_area);
-    p.sk_flags = reinterpret_cast<unsigned*>(sk_area + 256);
-    p.sk_partial = reinterpret_cast<float*>(sk_area + kSkHeaderBytes);
-  }
-  const dim3 grid(2 * clusters), block(GEMM3_THREADS);
-#define SYL_LAUNCH_GEMM3(SK, RES)                                                                                           \
-  launch_pdl(gemm3_tc_kernel<SK, RES>, grid, block, GEMM2_SMEM_TOTAL, st, op.a_hi, op.a_lo, b_hi, b_lo, op.o3_f32, op.o3_hi, \
-             op.o3_lo, p)
-  if (p.res_hi) {
-    if (sk) SYL_LAUNCH_GEMM3(true, true); else SYL_LAUNCH_GEMM3(false, true);
-  } else {
-    if (sk) SYL_LAUNCH_GEMM3(true, false); else SYL_LAUNCH_GEMM3(false, false);
-  }
-#undef SYL_LAUNCH_GEMM3
+  launch_pdl(gemm3_tc_kernel, dim3(2 * clusters), dim3(GEMM3_THREADS), GEMM2_SMEM_TOTAL, st, op.a_hi, op.a_lo, b_hi, b_lo, op.o3_f32,
+             op.o3_hi, op.o3_lo, p);
   return launch_ok() ? SYL_OK : SYL_E_CUDA;
 }
 
 int launch_gemm(syl_handle* h, const GemmOp& op, cudaStream_t st, int sm_count) {
-  // the scratch area belongs to the plan in use: forwards on different streams never share a plan
-  uint8_t* sk = h->sk_pool ? h->sk_pool + (size_t)h->plan_cur * h->sk_area : nullptr;
-  if (launch_gemm3_raw(op, op.w->map2_hi, op.w->map2_lo, st, sm_count, sk) != SYL_OK)
+  if (launch_gemm3_raw(op, op.w->map2_hi, op.w->map2_lo, st, sm_count) != SYL_OK)
     return fail(h, SYL_E_CUDA, "gemm launch failed: %s", launch_err());
   return SYL_OK;
 }
 
 // single-pass mode pairs taps into N = 96 MMAs (posconv.cuh); SYL_POSCONV_PAIR=0 keeps one tap per MMA (A/B timing)
+#ifdef SYL_DIAG
 bool posconv_pair_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SYL_POSCONV_PAIR");
-    v = e ? atoi(e) : 1;
-  }
+  static const int v = diag_env("SYL_POSCONV_PAIR", 1);
   return v != 0;
 }
+#else
+constexpr bool posconv_pair_enabled() { return true; }
+#endif
 
 int launch_posconv(syl_handle* h, const PosOp& op, cudaStream_t st, int sm_count) {
   const bool pair = op.p.n_pass == 1 && posconv_pair_enabled();
@@ -659,19 +619,23 @@ int launch_posconv(syl_handle* h, const PosOp& op, cudaStream_t st, int sm_count
   return SYL_OK;
 }
 
-bool g_attrs_set = false;
+// cudaFuncSetAttribute applies to the CURRENT device's copy of the function, so the >48 KB dynamic shared memory
+// opt-in is made once per device (a second handle on cuda:1 in the same process needs its own), under a lock.
+std::mutex g_attr_mutex;
+uint64_t g_attrs_set_mask = 0;       // bit d: attributes set on device d
 int ensure_attrs(syl_handle* h) {
-  if (g_attrs_set) return SYL_OK;
-  CUDA_TRY(h, (cudaFuncSetAttribute(gemm3_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL)));
-  CUDA_TRY(h, (cudaFuncSetAttribute(gemm3_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL)));
-  CUDA_TRY(h, (cudaFuncSetAttribute(gemm3_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL)));
-  CUDA_TRY(h, (cudaFuncSetAttribute(gemm3_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL)));
+  std::lock_guard<std::mutex> lock(g_attr_mutex);
+  const int d = h ? h->device : 0;
+  if (d < 64 && (g_attrs_set_mask >> d) & 1) return SYL_OK;
+  CUDA_TRY(h, cudaFuncSetAttribute(gemm3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL));
   CUDA_TRY(h, cudaFuncSetAttribute(posconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM_TOTAL));
   CUDA_TRY(h, cudaFuncSetAttribute(posconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM_TOTAL));
   CUDA_TRY(h, (cudaFuncSetAttribute(attention7_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL)));
   CUDA_TRY(h, (cudaFuncSetAttribute(attention7_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL)));
+#ifdef SYL_DIAG
   CUDA_TRY(h, (cudaFuncSetAttribute(attention7_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL)));
-  g_attrs_set = true;
+#endif
+  if (d < 64) g_attrs_set_mask |= uint64_t(1) << d;
   return SYL_OK;
 }
 
@@ -680,8 +644,11 @@ int posconv_base_offset_mode() {
   // shared-memory address, exactly like TMA's, so a descriptor whose start is shifted by whole 128-byte rows needs
   // base_offset = 0.  Setting (addr >> 7) & 7 there produces wrong results.  The env var only exists to re-run
   // that experiment.
-  const char* e = getenv("SYL_POSCONV_BASE_OFFSET");
-  return e ? atoi(e) : 0;
+#ifdef SYL_DIAG
+  return diag_env("SYL_POSCONV_BASE_OFFSET", 0);
+#else
+  return 0;
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -793,11 +760,6 @@ int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
       op.p.N = kH;
       op.p.n_pass = split_enc ? 3 : 1;
       op.p.bias = w.out.bias;
-      if (resid_epilogue_level() >= 2) {
-        op.p.res_hi = at<__half>(ws, L.h16_hi);
-        op.p.res_lo = at<__half>(ws, L.h16_lo);
-        op.p.res_ld = kH;
-      }
       if (!make_o_maps(h, op, at<float>(ws, L.pre), nullptr, nullptr, kH)) return SYL_E_CUDA;
     }
     {
@@ -819,11 +781,6 @@ int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
       op.p.N = kH;
       op.p.n_pass = split_enc ? 3 : 1;
       op.p.bias = w.ffn2.bias;
-      if (resid_epilogue_level() >= 1) {
-        op.p.res_hi = at<__half>(ws, L.h16_hi);
-        op.p.res_lo = at<__half>(ws, L.h16_lo);
-        op.p.res_ld = kH;
-      }
       if (!make_o_maps(h, op, at<float>(ws, L.pre), nullptr, nullptr, kH)) return SYL_E_CUDA;
     }
   }
@@ -843,11 +800,7 @@ int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
 template <int D>
 void launch_ln(const float* x, const float* add, const __half* add_hi, const __half* add_lo, const float* g, const float* b, int rows,
                float* of, __half* ohi, __half* olo, cudaStream_t st) {
-  static const int warps = [] {        // SYL_LN_WARPS=4: 128-thread blocks (A/B not run yet); the kernel is built for <= 256 threads
-    const char* e = getenv("SYL_LN_WARPS");
-    const int v = e ? atoi(e) : 8;
-    return (v == 2 || v == 4 || v == 8) ? v : 8;
-  }();
+  constexpr int warps = 8;   // rows per block; 2 and 4 measured equal (profiles/r03_variants_ab.md)
   launch_pdl(layernorm_rows_kernel<D>, dim3((rows + warps - 1) / warps), dim3(warps * 32), 0, st, x, add, add_hi, add_lo, g, b, rows, of,
              ohi, olo);
 }
@@ -868,21 +821,22 @@ int launch_attention(const CUtensorMap& qkv, const CUtensorMap& o_hi, const CUte
   ap.out_lo = out_lo;
   // experiment switches (profiles/r02_attention.md): SYL_ATTN_POLY = exp2 pairs (out of every four) computed on the
   // FMA pipe (0 or 1), SYL_ATTN_DEBUG = arithmetic-removal probes
-  static int init = 0, debug = 0, poly = 1;
-  if (!init) {
-    const char* e = getenv("SYL_ATTN_DEBUG");
-    debug = e ? atoi(e) : 0;
-    e = getenv("SYL_ATTN_POLY");
-    poly = e ? atoi(e) : 1;
-    init = 1;
-  }
+#ifdef SYL_DIAG
+  static const int debug = diag_env("SYL_ATTN_DEBUG", 0), poly = diag_env("SYL_ATTN_POLY", 1);
+#else
+  constexpr int debug = 0, poly = 1;
+#endif
   ap.debug = debug;
   const int q_tiles = (T + ATT_BQ - 1) / ATT_BQ;
   const int items = B * kHeads * ((q_tiles + ATT_QT - 1) / ATT_QT);
   const int grid = std::min(items, sm_count);
-  if (ap.trace)
+#ifdef SYL_DIAG
+  if (ap.trace) {
     launch_pdl(attention7_kernel<0, true>, dim3(grid), dim3(ATT7_THREADS), ATT7_SMEM_TOTAL, st, qkv, o_hi, o_lo, ap);
-  else if (poly == 1)
+    return launch_ok() ? SYL_OK : SYL_E_CUDA;
+  }
+#endif
+  if (poly == 1)
     launch_pdl(attention7_kernel<1, false>, dim3(grid), dim3(ATT7_THREADS), ATT7_SMEM_TOTAL, st, qkv, o_hi, o_lo, ap);
   else
     launch_pdl(attention7_kernel<0, false>, dim3(grid), dim3(ATT7_THREADS), ATT7_SMEM_TOTAL, st, qkv, o_hi, o_lo, ap);
@@ -902,15 +856,8 @@ int run_frontend(syl_handle* h, const float* wav, cudaStream_t st) {
                at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift));
     __half* hi = at<__half>(ws, L.act_hi[0]);
     __half* lo = conv_split(h->mode, 1) ? at<__half>(ws, L.act_lo[0]) : nullptr;
-    static const int conv0_mb = [] {     // SYL_CONV0_MB=5: 48-register build, 5 blocks per SM (frontend.cuh)
-      const char* e = getenv("SYL_CONV0_MB");
-      return e ? atoi(e) : 4;
-    }();
     if (lo)
       launch_pdl(conv0_mma_kernel<true>, dim3((L0 + C0M_T - 1) / C0M_T, B), dim3(C0M_THREADS), 0, st, wav, pl.t_samp, L0,
-                 h->conv0_bfrag, at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift), hi, lo);
-    else if (conv0_mb == 5)
-      launch_pdl(conv0_mma_kernel<false, 5>, dim3((L0 + C0M_T - 1) / C0M_T, B), dim3(C0M_THREADS), 0, st, wav, pl.t_samp, L0,
                  h->conv0_bfrag, at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift), hi, lo);
     else
       launch_pdl(conv0_mma_kernel<false>, dim3((L0 + C0M_T - 1) / C0M_T, B), dim3(C0M_THREADS), 0, st, wav, pl.t_samp, L0,
@@ -954,8 +901,7 @@ int run_layer(syl_handle* h, int l, float* h_out, cudaStream_t st) {
   }
   {
     StageTimer tm(h, ST_LN, st);   // h = LN(h + attn); the residual stream is the fp16 pair (h16_hi, h16_lo), in place
-    const bool fused = pl.out[l].p.res_hi != nullptr;   // the out-projection epilogue already added the residual
-    launch_ln<kH>(at<float>(ws, L.pre), nullptr, fused ? nullptr : at<__half>(ws, L.h16_hi), fused ? nullptr : at<__half>(ws, L.h16_lo),
+    launch_ln<kH>(at<float>(ws, L.pre), nullptr, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo),
                   w.ln1_g, w.ln1_b, M, nullptr, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), st);
   }
   {
@@ -968,8 +914,7 @@ int run_layer(syl_handle* h, int l, float* h_out, cudaStream_t st) {
   }
   {
     StageTimer tm(h, ST_LN, st);   // h = LN(h + ffn); fp32 only where the caller wants the layer output (h_out)
-    const bool fused = pl.ffn2[l].p.res_hi != nullptr;
-    launch_ln<kH>(at<float>(ws, L.pre), nullptr, fused ? nullptr : at<__half>(ws, L.h16_hi), fused ? nullptr : at<__half>(ws, L.h16_lo),
+    launch_ln<kH>(at<float>(ws, L.pre), nullptr, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo),
                   w.ln2_g, w.ln2_b, M, h_out, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), st);
   }
   CUDA_TRY(h, cudaGetLastError());
@@ -987,6 +932,7 @@ int run_segment(const float* states, int B, int T, float thr_norm, float thr_mer
 
 }  // namespace
 
+#ifdef SYL_DIAG
 template <int N>
 static int run_mma_probe(int iters, int ctas, long long* out_dev, cudaStream_t st) {
   if (cudaFuncSetAttribute(mma_probe_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 1024 + 64) != cudaSuccess)
@@ -994,6 +940,7 @@ static int run_mma_probe(int iters, int ctas, long long* out_dev, cudaStream_t s
   mma_probe_kernel<N><<<ctas, 128, 65536 + 1024 + 64, st>>>(iters, out_dev);
   return launch_ok() ? SYL_OK : SYL_E_CUDA;
 }
+#endif
 
 // ================================================================================================
 // exported C ABI
@@ -1019,7 +966,6 @@ int syl_create(syl_handle** out, int device, int n_layers, int mode) {
   if (prop.major != 10)
     return fail(nullptr, SYL_E_CUDA, "syl_create: device %d is sm_%d%d; this library contains sm_100a code only", device,
                 prop.major, prop.minor);
-  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, SYL_E_CUDA, "cudaSetDevice failed");
   syl_handle* h = new syl_handle();
   h->device = device;
   h->n_layers = n_layers;
@@ -1033,21 +979,25 @@ int syl_create(syl_handle** out, int device, int n_layers, int mode) {
 
 void syl_destroy(syl_handle* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  {
+  DeviceGuard dg(h->device);
   for (auto& kv : h->raw) cudaFree(kv.second.first);
   for (void* p : h->owned) cudaFree(p);
   for (cudaEvent_t e : h->pool) cudaEventDestroy(e);
   for (Plan& pl : h->plans)
     for (auto& g : pl.graphs) cudaGraphExecDestroy(g.exec);
   (void)cudaGetLastError();   // teardown never leaves a pending error for the next runtime user of this thread
+  }
   delete h;
 }
 
 int syl_load_weight(syl_handle* h, const char* name, const void* dev_ptr, const int64_t* shape, int ndim, int dtype) {
   if (!h || !name || !dev_ptr || !shape || ndim < 1 || ndim > 4) return fail(h, SYL_E_ARG, "syl_load_weight: bad arguments");
+  std::lock_guard<std::mutex> lock(h->mu);
   if (dtype != SYL_DTYPE_F32) return fail(h, SYL_E_ARG, "syl_load_weight: only fp32 tensors are accepted");
   if (h->finalized) return fail(h, SYL_E_STATE, "syl_load_weight after syl_finalize");
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  DeviceGuard dg(h->device);
+  if (dg.err != cudaSuccess) return fail(h, SYL_E_CUDA, "cudaSetDevice(%d): %s", h->device, cudaGetErrorString(dg.err));
   size_t n = 1;
   std::vector<int64_t> shp(shape, shape + ndim);
   for (int64_t d : shp) n *= (size_t)d;
@@ -1068,16 +1018,12 @@ int syl_load_weight(syl_handle* h, const char* name, const void* dev_ptr, const 
 int syl_finalize(syl_handle* h) {
   SYL_ENTER();
   if (!h) return SYL_E_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
   if (h->finalized) return SYL_OK;
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  DeviceGuard dg(h->device);
+  if (dg.err != cudaSuccess) return fail(h, SYL_E_CUDA, "cudaSetDevice(%d): %s", h->device, cudaGetErrorString(dg.err));
   int rc = ensure_attrs(h);
   if (rc) return rc;
-  if (streamk_enabled() && !h->sk_pool) {
-    h->sk_area = streamk_area_bytes(h->sm_count);
-    const size_t bytes = h->sk_area * syl_handle::kPlans;
-    if (!(h->sk_pool = dev_alloc<uint8_t>(h, bytes))) return fail(h, SYL_E_CUDA, "cudaMalloc of the stream-K scratch pool failed");
-    CUDA_TRY(h, cudaMemset(h->sk_pool, 0, bytes));   // tickets and flags start at zero and return to zero after every launch
-  }
   const std::string fe = "feature_extractor.conv_layers.";
   if (!(h->conv0_w = copy_vec(h, fe + "0.conv.weight", (size_t)kC * 10))) return SYL_E_STATE;
   if (!(h->conv0_bfrag = dev_alloc<uint4>(h, 64 * 32))) return fail(h, SYL_E_CUDA, "cudaMalloc failed");
@@ -1219,6 +1165,7 @@ int syl_forward(syl_handle* h, const float* wav, const int32_t* n_samples, int b
                 void* workspace, size_t workspace_bytes, void* stream) {
   SYL_ENTER();
   if (!h) return SYL_E_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
   if (!h->finalized) return fail(h, SYL_E_STATE, "syl_forward before syl_finalize");
   if (!wav || !hidden || !workspace || batch <= 0) return fail(h, SYL_E_ARG, "syl_forward: null pointer or empty batch");
   if (t_samp_max < 400) return fail(h, SYL_E_ARG, "syl_forward: need at least 400 samples (one frame), got %d", t_samp_max);
@@ -1226,7 +1173,8 @@ int syl_forward(syl_handle* h, const float* wav, const int32_t* n_samples, int b
   if (workspace_bytes < need) return fail(h, SYL_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
   if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return fail(h, SYL_E_ARG, "workspace must be 1024-byte aligned");
   if (seg && (!seg_count || max_seg <= 0)) return fail(h, SYL_E_ARG, "syl_forward: seg needs seg_count and max_seg > 0");
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  DeviceGuard dg(h->device);
+  if (dg.err != cudaSuccess) return fail(h, SYL_E_CUDA, "cudaSetDevice(%d): %s", h->device, cudaGetErrorString(dg.err));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int rc = build_plan(h, batch, t_samp_max, workspace, hidden);
   if (rc) return rc;
@@ -1289,11 +1237,13 @@ int syl_conv_frontend(syl_handle* h, const float* wav, int batch, int t_samp_max
                       size_t workspace_bytes, void* stream) {
   SYL_ENTER();
   if (!h) return SYL_E_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
   if (!h->finalized) return fail(h, SYL_E_STATE, "syl_conv_frontend before syl_finalize");
   if (!wav || !feats || !workspace || batch <= 0 || t_samp_max < 400) return fail(h, SYL_E_ARG, "syl_conv_frontend: bad arguments");
   const size_t need = syl_workspace_bytes(h, batch, t_samp_max);
   if (workspace_bytes < need) return fail(h, SYL_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  DeviceGuard dg(h->device);
+  if (dg.err != cudaSuccess) return fail(h, SYL_E_CUDA, "cudaSetDevice(%d): %s", h->device, cudaGetErrorString(dg.err));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int rc = build_plan(h, batch, t_samp_max, workspace, nullptr);
   if (rc) return rc;
@@ -1308,6 +1258,7 @@ int syl_encoder_layer(syl_handle* h, int layer, const float* h_in, const int32_t
                       float* h_out, void* workspace, size_t workspace_bytes, void* stream) {
   SYL_ENTER();
   if (!h) return SYL_E_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
   if (!h->finalized) return fail(h, SYL_E_STATE, "syl_encoder_layer before syl_finalize");
   if (!h_in || !h_out || !workspace || batch <= 0 || T <= 0 || layer < 0 || layer >= h->n_layers)
     return fail(h, SYL_E_ARG, "syl_encoder_layer: bad arguments");
@@ -1316,7 +1267,8 @@ int syl_encoder_layer(syl_handle* h, int layer, const float* h_in, const int32_t
   for (int i = 6; i >= 0; --i) n = (n - 1) * kConvS[i] + kConvK[i];
   const size_t need = syl_workspace_bytes(h, batch, n);
   if (workspace_bytes < need) return fail(h, SYL_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  DeviceGuard dg(h->device);
+  if (dg.err != cudaSuccess) return fail(h, SYL_E_CUDA, "cudaSetDevice(%d): %s", h->device, cudaGetErrorString(dg.err));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int rc = build_plan(h, batch, n, workspace, nullptr);
   if (rc) return rc;
@@ -1336,8 +1288,11 @@ int syl_attention(const void* qkv_f16, const int32_t* kv_len, int batch, int T, 
   std::string err;
   if (!qkv_f16 || !out_f16 || batch <= 0 || T <= 0) return fail(nullptr, SYL_E_ARG, "syl_attention: bad arguments");
   if (cudaFuncSetAttribute(attention7_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL) != cudaSuccess ||
-      cudaFuncSetAttribute(attention7_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL) != cudaSuccess ||
-      cudaFuncSetAttribute(attention7_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL) != cudaSuccess)
+      cudaFuncSetAttribute(attention7_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL) != cudaSuccess
+#ifdef SYL_DIAG
+      || cudaFuncSetAttribute(attention7_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT7_SMEM_TOTAL) != cudaSuccess
+#endif
+  )
     return fail(nullptr, SYL_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
   CUtensorMap map, omap;
   uint64_t dims[3] = {(uint64_t)3 * kH, (uint64_t)T, (uint64_t)batch};
@@ -1354,6 +1309,7 @@ int syl_attention(const void* qkv_f16, const int32_t* kv_len, int batch, int T, 
   return SYL_OK;
 }
 
+#ifdef SYL_DIAG
 int syl_attention_trace(const void* qkv_f16, const int32_t* kv_len, int batch, int T, void* out_f16, void* trace_dev,
                         int trace_cap, void* stream) {
   if (!trace_dev || trace_cap <= 0) return fail(nullptr, SYL_E_ARG, "syl_attention_trace: bad arguments");
@@ -1364,6 +1320,7 @@ int syl_attention_trace(const void* qkv_f16, const int32_t* kv_len, int batch, i
   g_attn_trace_cap = 0;
   return rc;
 }
+#endif
 
 size_t syl_pcm16_workspace_bytes(int batch, int t_samp_max) {
   if (batch <= 0 || t_samp_max <= 0) return 0;
@@ -1486,29 +1443,15 @@ int syl_gemm_f32(const float* A, const float* W, const float* bias, const float*
   CUtensorMap b2_hi, b2_lo;     // this CTA's half of the B tile
   if (!make_tmap_f16(&b2_hi, w_hi, 2, wd, wsd, 128, &err) || !make_tmap_f16(&b2_lo, w_lo, 2, wd, wsd, 128, &err))
     return fail(nullptr, SYL_E_CUDA, "%s", err.c_str());
-  if (cudaFuncSetAttribute(gemm3_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL) != cudaSuccess)
+  if (cudaFuncSetAttribute(gemm3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL) != cudaSuccess)
     return fail(nullptr, SYL_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
-  uint8_t* sk = nullptr;
-  if (streamk_enabled()) {
-    // test hook for the stream-K schedule: one process-wide scratch area (calls through this entry point are not concurrent)
-    static uint8_t* area = nullptr;
-    if (!area) {
-      const size_t bytes = streamk_area_bytes(sms);
-      if (cudaMalloc(&area, bytes) != cudaSuccess || cudaMemset(area, 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
-        area = nullptr;
-        return fail(nullptr, SYL_E_CUDA, "stream-K scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
-      }
-    }
-    sk = area;
-    if (cudaFuncSetAttribute(gemm3_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_TOTAL) != cudaSuccess)
-      return fail(nullptr, SYL_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
-  }
-  if (launch_gemm3_raw(op, b2_hi, b2_lo, st, sms, sk) != SYL_OK)
+  if (launch_gemm3_raw(op, b2_hi, b2_lo, st, sms) != SYL_OK)
     return fail(nullptr, SYL_E_CUDA, "gemm launch failed: %s", launch_err());
   if (residual) add_inplace_kernel<<<grid_for((size_t)M * N), 256, 0, st>>>(out, residual, (size_t)M * N);
   return launch_ok() ? SYL_OK : fail(nullptr, SYL_E_CUDA, "launch failed: %s", launch_err());
 }
 
+#ifdef SYL_DIAG
 int syl_mma_probe(int n, int iters, int ctas, void* cycles_out_dev, void* stream) {
   SYL_ENTER();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1524,6 +1467,7 @@ int syl_mma_probe(int n, int iters, int ctas, void* cycles_out_dev, void* stream
     default: return SYL_E_ARG;
   }
 }
+#endif
 
 int syl_powf_half(const float* x, float* y, int64_t n, void* stream) {
   SYL_ENTER();
@@ -1544,6 +1488,7 @@ int syl_profile_enable(syl_handle* h, int on) {
 
 int syl_profile_read(syl_handle* h, float* ms, int* counts) {
   if (!h || !ms || !counts) return SYL_E_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
   for (int i = 0; i < ST_COUNT; ++i) {
     ms[i] = 0.0f;
     counts[i] = 0;
@@ -1563,6 +1508,8 @@ int syl_profile_read(syl_handle* h, float* ms, int* counts) {
 int syl_read_stage(syl_handle* h, const char* name, float* out, size_t n_floats, void* stream) {
   SYL_ENTER();
   if (!h || !name || !out) return SYL_E_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard dg(h->device);
   if (!h->plans[h->plan_cur].valid) return fail(h, SYL_E_STATE, "syl_read_stage: no forward has run yet");
   const Plan& pl = h->plans[h->plan_cur];
   const WsLayout& L = pl.lay;

@@ -153,10 +153,10 @@ __global__ void conv0_bfrag_kernel(const float* __restrict__ w0, uint4* __restri
   tab[i] = v;
 }
 
-// kMinBlocks: 4 (64 registers, 32 warps per SM) is the measured build; 5 (48 registers, 28 bytes of spills, 40 warps per
-// SM) exists for an A/B that has not been run yet (SYL_CONV0_MB=5): the kernel issues only 56 % of its slots.
-template <bool kLo, int kMinBlocks = 4>
-__global__ void __launch_bounds__(C0M_THREADS, kMinBlocks)
+// 4 blocks per SM (64 registers, 32 warps per SM).  A 5-block build (48 registers, 28 bytes of spills, 40 warps) was
+// measured slower, 0.429 vs 0.410 ms (profiles/r03_variants_ab.md), and removed.
+template <bool kLo>
+__global__ void __launch_bounds__(C0M_THREADS, 4)
 conv0_mma_kernel(const float* __restrict__ wav, int t_samp, int L0, const uint4* __restrict__ bfrag,
                  const float* __restrict__ scale, const float* __restrict__ shift, __half* __restrict__ out_hi,
                  __half* __restrict__ out_lo) {

@@ -23,42 +23,6 @@ constexpr int GEMM3_THREADS = (GEMM_EPI_WARP0 + GEMM3_EPI_WARPS) * 32;   // 640
 constexpr int GEMM3_EPI_STAGE_BYTES = 2048;
 static_assert(GEMM3_EPI_WARPS * GEMM3_EPI_STAGE_BYTES == GEMM2_EPI_BYTES, "staging area");
 
-// Stream-K scheduling (template flag kSK; switched on per launch by the host, api.cu gemm_streamk_wanted).  The
-// data-parallel schedule hands out whole 256 x 256 tiles round robin, so 192 tiles on 74 clusters (out-projection,
-// FFN2, feature projection at batch 32 x 10 s) cost three full rounds for 2.6 rounds of work.  With kSK the unit of
-// work is one k-block of one tile: cluster c owns the units [c U / C, (c + 1) U / C) of the U = tiles x k-blocks, i.e.
-// at most one tile whose first k-blocks belong to cluster c - 1 ("tail" item), whole tiles, and at most one tile
-// whose last k-blocks belong to cluster c + 1 ("head" item).  A cluster walks its range BACKWARDS: the head item
-// comes first and its raw fp32 accumulator goes to this cluster's 256 KB slot of the scratch area (every epilogue
-// warp writes the [32 x 64] block it would have stored, coalesced, and raises its own flag); the tail item comes last
-// and its epilogue adds the slot of cluster c - 1 before bias / activation / stores.  Who waits for whom:
-//   * cluster ids are start-order tickets (one atomicAdd per cluster, reset by the last taker), so cluster c - 1 is
-//     running when c exists, and producing a head item waits for nothing: no deadlock even when other kernels hold
-//     SMs and the clusters of one launch are not all resident;
-//   * flags go 0 -> 1 (producer warp) -> 0 (the one consumer warp), so a scratch area is reusable by the next launch
-//     on the same stream without a memset and CUDA-graph replays need no per-launch argument;
-//   * the sum is always (tail accumulator + head partial): results are deterministic run to run, but differ in the
-//     last bits from the data-parallel schedule, which adds all k-blocks in one accumulator.
-struct Gemm3Item {
-  int tile, kb0, kb1;
-};
-constexpr int GEMM3_SK_SLOT_FLOATS = 2 * GEMM3_EPI_WARPS * 32 * 64;   // one cluster's partial tile, 256 KB
-constexpr int GEMM3_SK_FLAGS_PER_CLUSTER = 2 * GEMM3_EPI_WARPS;       // one flag per epilogue warp of either CTA
-
-__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// kRes: the epilogue adds a residual given as an fp16 pair (hi + lo, the encoder's residual stream) to acc + bias, so
-// the LayerNorm after the out-projection / FFN2 reads one tensor instead of two (same 12 bytes per element in total,
-// but 4 of them move into a kernel that is not HBM bound).  The sum is formed exactly as the LayerNorm forms it,
-// (acc + bias) + (hi + lo), so results are bit-identical to the unfused path.  Off by default (SYL_RESID_EPI).
-template <bool kSK, bool kRes>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM3_THREADS, 1)
 gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__ CUtensorMap a_lo,
                const __grid_constant__ CUtensorMap b_hi, const __grid_constant__ CUtensorMap b_lo,
@@ -83,21 +47,11 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int tiles_m_per_batch = (p.rows_per_batch + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);   // 256-row cluster tiles
-  int cluster_id = blockIdx.x >> 1;
+  const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
   const int tiles_n = p.N / GEMM_BLOCK_N;
   const int num_tiles = p.batches * tiles_m_per_batch * tiles_n;
   const int kb_total = p.kb_per_pass * p.n_pass;
-  if constexpr (kSK) {
-    // start-order ticket instead of blockIdx: the leader draws it, the peer reads it from the leader's shared memory
-    // after the cluster barrier below (the host does not combine kSK with programmatic dependent launch: the ticket
-    // is drawn before griddepcontrol.wait)
-    if (leader && threadIdx.x == 0) {
-      const uint32_t t = atomicAdd(p.sk_ticket, 1u);
-      if (t == (uint32_t)num_clusters - 1) atomicExch(p.sk_ticket, 0u);   // every ticket of this launch is drawn
-      tmem_ptr[1] = t;
-    }
-  }
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&a_hi);
@@ -125,35 +79,6 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
   cluster_sync_all();                        // barriers of both CTAs are initialised before anyone touches them
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
-  int unit_lo = 0, unit_hi = 0;              // kSK: this cluster's k-block units [unit_lo, unit_hi)
-  if constexpr (kSK) {
-    uint32_t t;
-    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(t) : "r"(mapa_shared(smem_u32(tmem_ptr + 1), 0)) : "memory");
-    cluster_id = (int)t;
-    const long long units = (long long)num_tiles * kb_total;
-    unit_lo = (int)(units * cluster_id / num_clusters);
-    unit_hi = (int)(units * (cluster_id + 1) / num_clusters);
-  }
-  // the schedule every role walks: whole tiles round robin, or (kSK) the unit range from its end to its start
-  int sched_pos = kSK ? unit_hi : cluster_id;
-  auto next_item = [&](Gemm3Item& item) -> bool {
-    if constexpr (kSK) {
-      if (sched_pos <= unit_lo) return false;
-      item.tile = (sched_pos - 1) / kb_total;
-      const int t0 = item.tile * kb_total;
-      const int lo = max(t0, unit_lo);
-      item.kb0 = lo - t0;
-      item.kb1 = sched_pos - t0;
-      sched_pos = lo;
-    } else {
-      if (sched_pos >= num_tiles) return false;
-      item.tile = sched_pos;
-      item.kb0 = 0;
-      item.kb1 = kb_total;
-      sched_pos += num_clusters;
-    }
-    return true;
-  };
   griddep_wait();                            // the predecessor kernel's output (our A operand, valid_rows) is complete
 
   if (warp == 0) {
@@ -161,14 +86,12 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      Gemm3Item item;
-      while (next_item(item)) {
-        const int tile = item.tile;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int n_tile = tile % tiles_n;
         const int m_tile = tile / tiles_n;
         const int batch = m_tile / tiles_m_per_batch;
         const int row0 = (m_tile % tiles_m_per_batch) * 2 * GEMM_BLOCK_M + (int)cta_rank * GEMM_BLOCK_M;
-        for (int kb = item.kb0; kb < item.kb1; ++kb) {
+        for (int kb = 0; kb < kb_total; ++kb) {
           const int pass = kb / p.kb_per_pass;
           const int kk = kb - pass * p.kb_per_pass;
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -194,12 +117,11 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      Gemm3Item item;
-      while (next_item(item)) {
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + acc * GEMM_BLOCK_N;
-        for (int kb = item.kb0; kb < item.kb1; ++kb) {
+        for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
           const uint64_t adesc = make_desc_k_sw128(smem_u32(smem_a + stage * GEMM2_A_BYTES));
@@ -207,7 +129,7 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
             // advancing K by 16 fp16 = 32 bytes inside the 128B swizzle row: +2 in 16-byte units
-            umma_f16_ss_2cta(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - item.kb0) | k) != 0);
+            umma_f16_ss_2cta(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
           umma_commit_2cta(&empty_bar[stage]);  // frees this smem stage in both CTAs once the MMAs have read it
           if (++stage == GEMM2_STAGES) {
@@ -244,9 +166,7 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
       if (lane == 0) tma_store_wait_read();
       __syncwarp();
     };
-    Gemm3Item item;
-    for (; next_item(item); ++it) {
-      const int tile = item.tile;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int n_tile = tile % tiles_n;
       const int m_tile = tile / tiles_n;
       const int batch = m_tile / tiles_m_per_batch;
@@ -268,64 +188,11 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
       uint32_t r[2][16];
       tmem_ld_32x32b_x16(taddr0, r[0]);
       tmem_ld_wait();
-      // kSK: this warp's [32 x 64] block inside a cluster's scratch slot, laid out [step][column][lane]
-      const int sk_block = (((int)cta_rank * GEMM3_EPI_WARPS + ew) * 64) * 32 + lane;
-      if constexpr (kSK) {
-        if (item.kb1 < kb_total) {
-          // head item: the accumulator holds k-blocks [0, kb1) only - park it for the cluster that finishes the tile
-          float* dst = p.sk_partial + (size_t)cluster_id * GEMM3_SK_SLOT_FLOATS + sk_block;
-#pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            if (s + 1 < 4) tmem_ld_32x32b_x16(taddr0 + (s + 1) * 16, r[(s + 1) & 1]);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) __stcg(dst + (s * 16 + j) * 32, __uint_as_float(r[s & 1][j]));
-            if (s + 1 < 4) tmem_ld_wait();
-          }
-          tc_fence_before_sync();
-          __threadfence();                   // every lane's partial is visible device-wide before the flag goes up
-          __syncwarp();
-          if (lane == 0) {
-            mbar_arrive_remote(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
-            st_release_gpu(p.sk_flags + cluster_id * GEMM3_SK_FLAGS_PER_CLUSTER + (int)cta_rank * GEMM3_EPI_WARPS + ew, 1u);
-          }
-          if (++acc == 2) {
-            acc = 0;
-            acc_phase ^= 1;
-          }
-          continue;
-        }
-      }
-      const float* sk_src = nullptr;         // tail item: the partial of the cluster that ran the first k-blocks
-      uint32_t* sk_flag = nullptr;
-      if constexpr (kSK) {
-        if (item.kb0 > 0) {
-          sk_src = p.sk_partial + (size_t)(cluster_id - 1) * GEMM3_SK_SLOT_FLOATS + sk_block;
-          sk_flag = p.sk_flags + (cluster_id - 1) * GEMM3_SK_FLAGS_PER_CLUSTER + (int)cta_rank * GEMM3_EPI_WARPS + ew;
-          if (lane == 0) {
-            // the producer is running (ticket order) and its head item waits for nothing; the bound turns a protocol
-            // bug into a launch failure instead of a hung GPU
-            uint32_t polls = 0;
-            while (ld_acquire_gpu(sk_flag) == 0u) {
-              if (++polls > (1u << 22)) __trap();
-            }
-          }
-          __syncwarp();
-        }
-      }
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
         if (s + 1 < 4) tmem_ld_32x32b_x16(taddr0 + (s + 1) * 16, r[(s + 1) & 1]);   // prefetch the next 16 columns
         const int col0 = n_tile * GEMM_BLOCK_N + cb * 64 + s * 16;
         float v[16];
-        if constexpr (kSK) {
-          if (sk_src != nullptr) {
-            float part[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) part[j] = __ldcg(sk_src + (s * 16 + j) * 32);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) r[s & 1][j] = __float_as_uint(__uint_as_float(r[s & 1][j]) + part[j]);
-          }
-        }
         const float4* b4 = reinterpret_cast<const float4*>(sbias + cb * 64 + s * 16);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -339,25 +206,6 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
         if (p.act == 1) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) gelu_fast2(v[2 * i], v[2 * i + 1], v[2 * i], v[2 * i + 1]);
-        }
-        if constexpr (kRes) {
-          if (row_in_batch < p.rows_per_batch) {     // rows beyond the matrix are clipped by the TMA store, not by these loads
-            const size_t off = ((size_t)batch * p.rows_per_batch + row_in_batch) * p.res_ld + col0;
-            const uint4* hp = reinterpret_cast<const uint4*>(p.res_hi + off);
-            const uint4* lp = reinterpret_cast<const uint4*>(p.res_lo + off);
-            const uint4 hq[2] = {hp[0], hp[1]}, lq[2] = {lp[0], lp[1]};
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const uint32_t hw[4] = {hq[i].x, hq[i].y, hq[i].z, hq[i].w}, lw[4] = {lq[i].x, lq[i].y, lq[i].z, lq[i].w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
-                const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[j]));
-                v[8 * i + 2 * j] += hf.x + lf.x;
-                v[8 * i + 2 * j + 1] += hf.y + lf.y;
-              }
-            }
-          }
         }
         if (zero_row) {
 #pragma unroll
@@ -426,9 +274,6 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
-      if constexpr (kSK) {
-        if (sk_flag != nullptr && lane == 0) *reinterpret_cast<volatile uint32_t*>(sk_flag) = 0u;   // slot consumed
-      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;

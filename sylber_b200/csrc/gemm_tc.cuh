@@ -37,14 +37,6 @@ struct GemmParams {
   int act;                  // 0 none, 1 GELU
   float col_scale;          // tiles whose first column is < col_scale_limit are multiplied by col_scale
   int col_scale_limit;      // (multiple of 256)
-  // residual added in the epilogue (gemm3_tc_kernel<*, true> only): out = acc + bias + (res_hi + res_lo), fp16 pair [rows][res_ld]
-  const __half* res_hi;
-  const __half* res_lo;
-  int res_ld;
-  // stream-K scratch (gemm3_tc_kernel<true> only; see gemm3_tc.cuh): one area per plan, owned by the handle
-  float* sk_partial;        // [clusters][GEMM3_SK_SLOT_FLOATS]
-  unsigned* sk_flags;       // [clusters][GEMM3_SK_FLAGS_PER_CLUSTER], all zero between launches
-  unsigned* sk_ticket;      // [1], zero between launches
 };
 
 }  // namespace syl

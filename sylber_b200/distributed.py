@@ -9,6 +9,7 @@ length T_max (GroupNorm statistics run over padding), ranks first 
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -56,4 +57,103 @@ def unpack_segment_table(all_seg, all_cnt, n_items, world):
         for k in range(hi - lo):
             row = r * per_rank + k
             out.append(seg[row, :cnt[row]].astype("int64"))
+    return out
+
+
+def _comm_device(segmenter, group):
+    """NCCL moves device tensors, every other backend (gloo in the CPU tests) host tensors."""
+    backend = dist.get_backend(group)
+    return torch.device(segmenter.device) if "nccl" in str(backend) else torch.device("cpu")
+
+
+def segment_sharded(segmenter, wav_file=None, wav=None, in_second=True, group=None, local_input=False, pad_to=None,
+                    gather_features=False):
+    """`Segmenter.__call__` for a LIST of utterances sharded over the ranks of `group` (one process per GPU).
+
+    Every rank calls this collectively.  With `local_input=False` (default) every rank passes the same global list and
+    runs the contiguous block `shard_range(len(list), rank, world)`; with `local_input=True` each rank passes only its
+    own clips (global order = rank order).  The forward has no cross-utterance dependency, so the data path needs no
+    collective; what is exchanged is (1) with local input and no `pad_to`, the batch-wide maximum length - an
+    utterance's result depends on the padded length, so every rank pads to the T_max the single call
+    would use - and (2) the segment table: an all-gather of the per-utterance segment counts, then of the fixed-stride
+    (utterances, max count, 2) int32 table (a few KB over NCCL / NVSwitch).
+
+    Returns the list of result dicts of the WHOLE batch in global order on every rank: `segments` for every utterance
+    (bit-identical to what one process calling `segmenter(wav=whole_list)` returns - tests/test_gpu_sharded.py);
+    `segment_features` and `hidden_states` for the rank's own utterances and None for the others, unless
+    `gather_features=True`, which also all-gathers the (N, 768) segment features.  Hidden states stay sharded."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        out = segmenter(wav_file=wav_file, wav=wav, in_second=in_second, pad_to=pad_to)
+        return out if isinstance(out, list) else [out]
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    items = wav_file if wav_file is not None else wav
+    if not isinstance(items, (list, tuple)):
+        raise TypeError("segment_sharded shards a list of utterances; pass a list")
+    items = list(items)
+    dev = _comm_device(segmenter, group)
+    if local_input:
+        sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+        mine_n = torch.tensor([len(items)], dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sizes, mine_n, group=group)
+        sizes = [int(x) for x in sizes.cpu().tolist()]
+        mine = items
+    else:
+        sizes = [shard_range(len(items), r, world)[1] - shard_range(len(items), r, world)[0] for r in range(world)]
+        lo, hi = shard_range(len(items), rank, world)
+        mine = items[lo:hi]
+    # the padded length of the whole call
+    if wav_file is not None:
+        rows, _ = segmenter._prepare(mine, None) if mine else ([], True)
+        local_kw = {"wav": rows}
+        known_all = False
+    else:
+        local_kw = {"wav": mine}
+        known_all = not local_input
+    if pad_to is None:
+        if known_all:
+            pad_to = max(int(torch.as_tensor(w).shape[-1]) for w in items)
+        else:
+            local_max = max((int(torch.as_tensor(w).shape[-1]) for w in local_kw["wav"]), default=0)
+            pad_to = global_max_length(local_max, device=dev, group=group)
+    local = segmenter(in_second=False, pad_to=pad_to, **local_kw) if mine else []
+    # (1) counts, (2) fixed-stride table
+    per_rank = max(sizes)
+    cnt = torch.zeros(per_rank, dtype=torch.int32)
+    for k, r in enumerate(local):
+        cnt[k] = len(r["segments"])
+    all_cnt = torch.empty(world * per_rank, dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(all_cnt, cnt.to(dev), group=group)
+    all_cnt_h = all_cnt.cpu()
+    stride = max(int(all_cnt_h.max()), 1)
+    seg = torch.zeros((per_rank, stride, 2), dtype=torch.int32)
+    for k, r in enumerate(local):
+        n = int(cnt[k])
+        if n:
+            seg[k, :n] = torch.from_numpy(np.asarray(r["segments"], dtype=np.int32).reshape(-1, 2))
+    all_seg = torch.empty((world * per_rank, stride, 2), dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(all_seg, seg.to(dev), group=group)
+    all_seg_h = all_seg.cpu().numpy()
+    all_feat_h = None
+    if gather_features:
+        feat = torch.zeros((per_rank, stride, 768), dtype=torch.float32)
+        for k, r in enumerate(local):
+            n = int(cnt[k])
+            if n:
+                feat[k, :n] = torch.from_numpy(np.ascontiguousarray(r["segment_features"]))
+        all_feat = torch.empty((world * per_rank, stride, 768), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(all_feat, feat.to(dev), group=group)
+        all_feat_h = all_feat.cpu().numpy()
+    out = []
+    for r in range(world):
+        for k in range(sizes[r]):
+            row = r * per_rank + k
+            n = int(all_cnt_h[row])
+            s = all_seg_h[row, :n].astype(np.int64) if n > 0 else np.array([])
+            d = {"segments": s * 1.0 / 50 if in_second else s, "segment_features": None, "hidden_states": None}
+            if r == rank:
+                d["segment_features"] = local[k]["segment_features"]
+                d["hidden_states"] = local[k]["hidden_states"]
+            elif all_feat_h is not None:
+                d["segment_features"] = all_feat_h[row, :n].copy() if n > 0 else np.array([])
+            out.append(d)
     return out

@@ -537,14 +537,19 @@ class Segmenter:
         return results
 
     @torch.no_grad()
-    def __call__(self, wav_file=None, wav=None, in_second=True, pcm16=None, sample_rate=16000):
+    def __call__(self, wav_file=None, wav=None, in_second=True, pcm16=None, sample_rate=16000, pad_to=None):
         """Same contract as the reference: a dict (single input) or list of dicts with
         `segments` (N,2), `segment_features` (N,768) float32, `hidden_states` (T_max,768) float32.
 
         `pcm16=` (extension): one or a list of 1-D int16 arrays / tensors of mono PCM at `sample_rate` Hz.  Equivalent
         to the reference's file branch (x / 32768, resampling to 16 kHz if needed, then (w - mean) / std,
         sylber.py:83-87) with conversion, resampling, normalisation and padding done on the GPU (syl_prepare_pcm16,
-        syl_resample, syl_prepare_f32) - half the host->device bytes."""
+        syl_resample, syl_prepare_f32) - half the host->device bytes.
+
+        `pad_to=` (extension): pad the batch to at least this many 16 kHz samples instead of to its own longest clip.
+        An utterance's result depends on its samples and on the padded length only (conv-0 GroupNorm runs over the
+        padding), so a shard of a list padded to the WHOLE list's maximum reproduces the rows of the
+        single call bit for bit - this is what `sylber_b200.distributed.segment_sharded` passes."""
         pcm = int(sample_rate) if pcm16 is not None else 0
         if pcm:
             is_batch = isinstance(pcm16, (list, tuple))
@@ -564,12 +569,15 @@ class Segmenter:
         if pcm and pcm != 16000:                       # lengths count 16 kHz samples from here on
             g = math.gcd(pcm, 16000)
             lengths = [resampled_length(n, pcm // g, 16000 // g) for n in lengths]
+        if pad_to is not None and self.bucket_ratio:
+            raise ValueError("pad_to fixes the padded length of the whole call; it cannot be combined with bucket_ratio")
+        floor = int(pad_to) if pad_to is not None else 0
         if self.bucket_ratio:
             # opt-in deviation from the reference's padding semantics (batching.py): each bucket is padded to its own max
             buckets = plan_length_buckets(lengths, self.bucket_ratio, self.max_batch)
         else:
             buckets = [list(range(len(rows)))]
-        results = self._run_jobs(rows, lengths, [(idx, max(lengths[i] for i in idx)) for idx in buckets], pcm)
+        results = self._run_jobs(rows, lengths, [(idx, max(floor, max(lengths[i] for i in idx))) for idx in buckets], pcm)
         outputs = [{'segments': seg * 1.0 / FRAME_RATE if in_second else seg,
                     'segment_features': feat, 'hidden_states': hid} for seg, feat, hid in results]
         return outputs if is_batch else outputs[0]

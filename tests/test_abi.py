@@ -12,9 +12,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "sylber_b200.h")
 
 
-def _declared_functions():
+def _header_source(diag=False):
+    """The header without comments; the `#ifdef SYL_DIAG` blocks are dropped (product build) or kept (diag=True)."""
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    if not diag:
+        src = re.sub(r"#ifdef SYL_DIAG.*?#endif", "", src, flags=re.S)
+    return src
+
+
+def _declared_functions(diag=False):
+    src = _header_source(diag)
     return sorted(set(re.findall(r"\b(syl_[a-z0-9_]+)\s*\(", src)))
 
 
@@ -69,8 +77,7 @@ def test_product_does_not_import_oracle():
 def _header_prototypes():
     """{name: (return type, [parameter types])} parsed from the header, types reduced to a kind: 'ptr', 'int', 'float',
     'size_t', 'int64', 'void'."""
-    src = open(HEADER).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = _header_source()
     src = re.sub(r"//[^\n]*", "", src)
 
     def kind(t):
@@ -115,3 +122,17 @@ def test_ctypes_table_matches_header_prototypes():
         res, args = _lib.SIGNATURES[name]
         assert [ckind(a) for a in args] == params, (name, params, [ckind(a) for a in args])
         assert ckind(res) == ret, (name, ret, res)
+
+
+def test_product_library_has_no_diagnostics(lib):
+    """Experiment switches and diagnostic entry points live only in the -DSYL_DIAG build (ADVICE / VERDICT round 1):
+    the product library exports none of them and its sources read the environment only inside `#ifdef SYL_DIAG`."""
+    diag_only = set(_declared_functions(diag=True)) - set(_declared_functions())
+    assert diag_only == set(_lib.DIAG_SIGNATURES) == {"syl_attention_trace", "syl_mma_probe"}
+    for n in diag_only:
+        assert not hasattr(lib, n), n
+    csrc = os.path.join(ROOT, "sylber_b200", "csrc")
+    for f in os.listdir(csrc):
+        src = open(os.path.join(csrc, f)).read()
+        product = re.sub(r"#ifdef SYL_DIAG.*?#e(ndif|lse)", "", src, flags=re.S)
+        assert "getenv" not in product, f

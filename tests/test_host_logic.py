@@ -107,50 +107,3 @@ def test_device_exp2_polynomial_error_bound():
     got = np.ldexp(q.astype(np.float64), n.astype(np.int64))
     rel = np.abs(got / np.exp2(a.astype(np.float64)) - 1)
     assert rel.max() < 3.5e-6, rel.max()
-
-
-def _streamk_items(cluster, clusters, tiles, kb_total):
-    """The walk of gemm3_tc_kernel<true> (csrc/gemm3_tc.cuh, next_item): cluster `cluster` owns the k-block units
-    [c U / C, (c + 1) U / C) and visits them from the end of the range to its start, one (tile, kb0, kb1) item at a
-    time."""
-    units = tiles * kb_total
-    lo, pos = units * cluster // clusters, units * (cluster + 1) // clusters
-    items = []
-    while pos > lo:
-        tile = (pos - 1) // kb_total
-        t0 = tile * kb_total
-        start = max(t0, lo)
-        items.append((tile, start - t0, pos - t0))
-        pos = start
-    return items
-
-
-@pytest.mark.parametrize("tiles,kb_total", [(189, 12), (189, 48), (192, 8), (768, 12), (256, 48), (128, 48), (576, 12),
-                                            (75, 1), (147, 3), (4032, 24), (1000, 7)])
-def test_streamk_schedule_invariants(tiles, kb_total):
-    """What the kernel's fix-up protocol relies on, checked on the schedule arithmetic for the GEMM shapes of the
-    batch 32 x 10 s forward and a few odd ones (the host only selects the schedule when tiles > clusters):
-    every k-block of every tile is computed exactly once; a tile is cut at most once; a cluster's cut items are its
-    FIRST (a head: k-blocks [0, kb1), parked for the next cluster) and its LAST (a tail: k-blocks [kb0, end), which
-    adds the previous cluster's partial) and nothing in between; the tail of cluster c is the tile whose head
-    cluster c - 1 parked."""
-    clusters = 74
-    assert tiles > clusters
-    seen = np.zeros((tiles, kb_total), dtype=np.int32)
-    heads, tails = {}, {}
-    for c in range(clusters):
-        items = _streamk_items(c, clusters, tiles, kb_total)
-        assert items, "every cluster has work"
-        for i, (tile, kb0, kb1) in enumerate(items):
-            assert 0 <= kb0 < kb1 <= kb_total
-            seen[tile, kb0:kb1] += 1
-            assert not (kb0 > 0 and kb1 < kb_total), "an item is never cut on both sides"
-            if kb1 < kb_total:
-                assert i == 0, "a head item is the first thing a cluster does"
-                heads[c] = tile
-            if kb0 > 0:
-                assert i == len(items) - 1, "a tail item is the last thing a cluster does"
-                tails[c] = tile
-    assert (seen == 1).all()
-    assert 0 not in tails and clusters - 1 not in heads
-    assert {c + 1: t for c, t in heads.items()} == tails

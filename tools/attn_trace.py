@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from sylber_b200 import _lib
 import gpu_util as G
-lib = _lib.load_library()
+lib = _lib.load_diag_library()      # diagnostic build (-DSYL_DIAG): the product library has no trace / probe entry points
 dev = torch.device("cuda", 0)
 B, T = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (32, 499)
 CAP = 4096

@@ -3,7 +3,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from sylber_b200 import _lib
 import gpu_util as G
-lib = _lib.load_library()
+lib = _lib.load_diag_library()      # diagnostic build (-DSYL_DIAG): the product library has no trace / probe entry points
 out = torch.zeros(1, dtype=torch.int64, device="cuda")
 for ctas in (1, 148):
     for n in (16, 32, 48, 64, 96, 128, 256):
