@@ -507,7 +507,7 @@ WsLayout make_layout(int batch, int t_samp) {
   w.gn_scale = take(B * kC * sizeof(float));
   w.gn_shift = take(B * kC * sizeof(float));
   w.valid = take(B * sizeof(int32_t));
-  w.nsq = take(M * sizeof(float));
+  w.nsq = take(2 * M * sizeof(float));   // squared norms, then their scalar powf (segment.cuh)
   w.seg_scratch = take(B * 6 * (size_t)(w.T + 1) * sizeof(int32_t));
   for (int i = 0; i < 6; ++i) {
     w.act_hi[i] = take(B * w.L[i] * kC * sizeof(__half));
@@ -924,8 +924,9 @@ int run_layer(syl_handle* h, int l, float* h_out, cudaStream_t st) {
 int run_segment(const float* states, int B, int T, float thr_norm, float thr_merge, int32_t* seg, int32_t* seg_count,
                 float* seg_feat, int max_seg, float* nsq, int32_t* scratch, cudaStream_t st) {
   const int rows = B * T;
-  launch_pdl(frame_sqnorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, states, rows, nsq);
-  launch_pdl(segment_kernel, dim3(B), dim3(32), 0, st, states, nsq, T, thr_norm, thr_merge, seg, seg_count, max_seg, scratch);
+  float* pw = nsq + rows;      // powf(nsq, .5f) per frame, right behind the squared norms
+  launch_pdl(frame_sqnorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, states, rows, nsq, pw);
+  launch_pdl(segment_kernel, dim3(B), dim3(32), 0, st, states, nsq, pw, T, thr_norm, thr_merge, seg, seg_count, max_seg, scratch);
   if (seg_feat) launch_pdl(segment_pool_kernel, dim3(max_seg, B), dim3(192), 0, st, states, T, seg, seg_count, max_seg, seg_feat);
   return launch_ok() ? SYL_OK : SYL_E_CUDA;
 }
@@ -1379,7 +1380,7 @@ int syl_kmeans_assign(const float* feats, int n, const float* centroids, int K, 
 
 size_t syl_segment_workspace_bytes(int batch, int T) {
   if (batch <= 0 || T <= 0) return 0;
-  return (((size_t)batch * T * sizeof(float) + 1023) & ~size_t(1023)) + (size_t)batch * 6 * (T + 1) * sizeof(int32_t);
+  return (((size_t)batch * T * 2 * sizeof(float) + 1023) & ~size_t(1023)) + (size_t)batch * 6 * (T + 1) * sizeof(int32_t);
 }
 
 int syl_segment(const float* states, int batch, int T, float thr_norm, float thr_merge, int32_t* seg,
@@ -1390,7 +1391,7 @@ int syl_segment(const float* states, int batch, int T, float thr_norm, float thr
   if (workspace_bytes < syl_segment_workspace_bytes(batch, T)) return SYL_E_WORKSPACE;
   float* nsq = reinterpret_cast<float*>(workspace);
   int32_t* scratch = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(workspace) +
-                                                (((size_t)batch * T * sizeof(float) + 1023) & ~size_t(1023)));
+                                                (((size_t)batch * T * 2 * sizeof(float) + 1023) & ~size_t(1023)));
   return run_segment(states, batch, T, thr_norm, thr_merge, seg, seg_count, seg_feat, max_seg, nsq, scratch,
                      reinterpret_cast<cudaStream_t>(stream));
 }

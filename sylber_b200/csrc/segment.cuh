@@ -11,7 +11,15 @@
 //   * `np.float32 ** .5` on a NumPy *scalar* is libm powf(x, .5f), not sqrtf: powf_half() below replays
 //     glibc's powf (FMA build, as selected on every AVX2 x86-64 host) in fp64, see powf_tables.cuh.
 // The scan over frames is inherently serial per utterance (each decision depends on the running centroid);
-// parallelism comes from one warp per utterance plus the 32 lanes over the 768 features.
+// parallelism comes from one warp per utterance plus the 32 lanes over the 768 features.  What bounds the scan is
+// therefore the LATENCY of one frame step, and the kernel is organised around that (round 3):
+//   * the rows of the utterance stream into a shared-memory ring by bulk async copies (cp.async.bulk + mbarrier)
+//     issued SEG_RING frames ahead, so no step waits on an L2 / HBM round trip;
+//   * powf(|x_i|^2 + eps, .5) of every frame is computed by the parallel norm kernel;
+//   * the merged centroid (curr * cnt + x) / (cnt + 1), its squared norm and the powf of that are computed
+//     speculatively, concurrently with the cosine that decides whether the merge happens;
+//   * the 24 divisions per lane by the small integer cnt + 1 use one reciprocal and Markstein's FMA correction
+//     (div_by_count below), which is the correctly rounded quotient - bit-identical to NumPy's division.
 #pragma once
 
 #include "common.cuh"
@@ -35,6 +43,39 @@ __device__ __forceinline__ void lane_load(LaneVec& d, const float* __restrict__ 
     const float2 t = *reinterpret_cast<const float2*>(row + seg_elem(lane, m));
     d.v[2 * m] = t.x;
     d.v[2 * m + 1] = t.y;
+  }
+}
+
+// 16-byte aligned global -> shared bulk copy whose bytes complete on an mbarrier (no tensor map needed)
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// a / n for n = float(small positive integer) with r = __frcp_rn(n): q0 = RN(a r), rem = a - q0 n (exact in one FMA),
+// q = RN(q0 + rem r).  Markstein's theorem: with a correctly rounded reciprocal this is the correctly rounded quotient
+// unless the significand of n is all ones (never for n <= 2^23) - provided nothing underflows, hence the guard.
+__device__ __forceinline__ float div_by_count(float a, float n, float r) {
+  const float q0 = __fmul_rn(a, r);
+  const float rem = __fmaf_rn(-q0, n, a);
+  const float q = __fmaf_rn(rem, r, q0);
+  return (fabsf(a) > 1e-30f) ? q : __fdiv_rn(a, n);
+}
+
+// shared-memory image of one row: the 8 pairwise blocks of 96 floats padded to 104 so that the 8 lane groups, which
+// read the same offset of different blocks, hit different banks
+constexpr int SEG_BLK_PAD = 104;
+constexpr int SEG_ROW_FLOATS = 8 * SEG_BLK_PAD;   // 832 floats = 3328 bytes
+constexpr int SEG_RING = 12;                      // rows in flight (40 KB)
+
+__device__ __forceinline__ void lane_load_smem(float (&v)[24], const float* row, int lane) {
+  const float* p = row + SEG_BLK_PAD * (lane >> 2) + 2 * (lane & 3);
+#pragma unroll
+  for (int m = 0; m < 12; ++m) {
+    const float2 t = *reinterpret_cast<const float2*>(p + 8 * m);
+    v[2 * m] = t.x;
+    v[2 * m + 1] = t.y;
   }
 }
 
@@ -106,10 +147,11 @@ __device__ float np_pairwise_serial(const float* a, int n) {
 __device__ __forceinline__ float np_sum_serial(const float* a, int n) { return __fadd_rn(0.0f, np_pairwise_serial(a, n)); }
 
 // ----------------------------------------------------------------------------------------------
-// per-frame squared norms + eps, one warp per frame:  nsq[i] = (x_i**2).sum() + 1e-8   (float32)
+// per-frame squared norms + eps, one warp per frame:  nsq[i] = (x_i**2).sum() + 1e-8   (float32), and
+// pw[i] = powf(nsq[i], .5f) - the denominator the scalar cossim of the scan uses for frame i (segment_utils.py:96)
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-frame_sqnorm_kernel(const float* __restrict__ states, int rows, float* __restrict__ nsq) {
+frame_sqnorm_kernel(const float* __restrict__ states, int rows, float* __restrict__ nsq, float* __restrict__ pw) {
   griddep_launch_dependents();
   griddep_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -118,7 +160,11 @@ frame_sqnorm_kernel(const float* __restrict__ states, int rows, float* __restric
   LaneVec x;
   lane_load(x, states + (size_t)row * SEG_D, lane);
   const float s = np_dot768(x, x);
-  if (lane == 0) nsq[row] = __fadd_rn(s, 1e-8f);
+  if (lane == 0) {
+    const float v = __fadd_rn(s, 1e-8f);
+    nsq[row] = v;
+    pw[row] = powf_half(v);
+  }
 }
 
 // mean over rows [s, e) in NumPy order; every lane keeps its 24 features
@@ -129,7 +175,18 @@ __device__ __forceinline__ void lane_mean_rows(LaneVec& acc, const float* __rest
     return;
   }
   lane_load(acc, states + (size_t)s * SEG_D, lane);
-  for (int r = s + 1; r < e; ++r) {
+  int r = s + 1;
+  for (; r + 3 < e; r += 4) {            // four rows of loads in flight, added in row order
+    LaneVec x0, x1, x2, x3;
+    lane_load(x0, states + (size_t)r * SEG_D, lane);
+    lane_load(x1, states + (size_t)(r + 1) * SEG_D, lane);
+    lane_load(x2, states + (size_t)(r + 2) * SEG_D, lane);
+    lane_load(x3, states + (size_t)(r + 3) * SEG_D, lane);
+#pragma unroll
+    for (int k = 0; k < SEG_PER_LANE; ++k)
+      acc.v[k] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc.v[k], x0.v[k]), x1.v[k]), x2.v[k]), x3.v[k]);
+  }
+  for (; r < e; ++r) {
     LaneVec x;
     lane_load(x, states + (size_t)r * SEG_D, lane);
 #pragma unroll
@@ -147,15 +204,17 @@ __device__ __forceinline__ void lane_mean_rows(LaneVec& acc, const float* __rest
 //   scratch [B, 6*(T+1)] int32/float workspace (segment starts/ends/dead flags, boundaries, sweep sims)
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32)
-segment_kernel(const float* __restrict__ states_all, const float* __restrict__ nsq_all, int T, float thr_norm,
-               float thr_merge, int32_t* __restrict__ seg_all, int32_t* __restrict__ seg_count, int max_seg,
+segment_kernel(const float* __restrict__ states_all, const float* __restrict__ nsq_all, const float* __restrict__ pw_all, int T,
+               float thr_norm, float thr_merge, int32_t* __restrict__ seg_all, int32_t* __restrict__ seg_count, int max_seg,
                int32_t* __restrict__ scratch_all) {
+  __shared__ __align__(128) float ring[SEG_RING][SEG_ROW_FLOATS];
+  __shared__ __align__(8) uint64_t full_bar[SEG_RING];
   griddep_launch_dependents();
-  griddep_wait();
   const int b = blockIdx.x;
   const int lane = lane_id();
   const float* states = states_all + (size_t)b * T * SEG_D;
   const float* nsq = nsq_all + (size_t)b * T;
+  const float* pw = pw_all + (size_t)b * T;
   int32_t* scratch = scratch_all + (size_t)b * 6 * (T + 1);
   int32_t* seg_s = scratch;
   int32_t* seg_e = scratch + (T + 1);
@@ -163,51 +222,105 @@ segment_kernel(const float* __restrict__ states_all, const float* __restrict__ n
   int32_t* mid_seg = scratch + 3 * (T + 1);
   float* sim_prev = reinterpret_cast<float*>(scratch + 4 * (T + 1));
   float* sim_next = reinterpret_cast<float*>(scratch + 5 * (T + 1));
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < SEG_RING; ++k) mbar_init(&full_bar[k], 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  griddep_wait();
+
+  // row `r` of the utterance -> ring slot r % SEG_RING: lane 0 arms the barrier, lanes 0..7 copy one 384-byte block each
+  auto prefetch = [&](int r) {
+    if (r >= T) return;
+    const int slot = r % SEG_RING;
+    if (lane == 0) mbar_arrive_expect_tx(&full_bar[slot], SEG_D * sizeof(float));
+    __syncwarp();
+    if (lane < 8) bulk_copy_g2s(&ring[slot][SEG_BLK_PAD * lane], states + (size_t)r * SEG_D + 96 * lane, 96 * sizeof(float), &full_bar[slot]);
+  };
+  for (int r = 0; r < SEG_RING; ++r) prefetch(r);
 
   int nseg = 0, nmid = 0;
   // ---- phase 1: greedy scan (segment_utils.py:79-108) ----
   {
-    LaneVec curr;
-    float curr_sq = 0.0f;  // (curr**2).sum() + 1e-8
+    float curr[SEG_PER_LANE];
+    float p_curr = 0.0f;   // powf((curr**2).sum() + 1e-8, .5f)
     int cnt = 0, s = -1;
-    for (int i = 0; i < T; ++i) {
-      const float xsq = nsq[i];
-      const bool on = __fsqrt_rn(xsq) >= thr_norm;    // array path: `** .5` on an ndarray is sqrt
-      if (!on) {
-        if (s > -1) {
-          if (lane == 0) { seg_s[nseg] = s; seg_e[nseg] = i; }
-          ++nseg;
+    for (int i0 = 0; i0 < T; i0 += 32) {
+      const int idx = min(i0 + lane, T - 1);
+      const float my_sq = nsq[idx], my_pw = pw[idx];
+      const int n_here = min(32, T - i0);
+      for (int j = 0; j < n_here; ++j) {
+        const int i = i0 + j;
+        const float xsq = __shfl_sync(0xffffffffu, my_sq, j), px = __shfl_sync(0xffffffffu, my_pw, j);
+        const int slot = i % SEG_RING;
+        mbar_wait(&full_bar[slot], (uint32_t)(i / SEG_RING) & 1u);
+        const bool on = __fsqrt_rn(xsq) >= thr_norm;    // array path: `** .5` on an ndarray is sqrt
+        if (!on) {
+          prefetch(i + SEG_RING);                        // the slot was never read: nothing to order
+          if (s > -1) {
+            if (lane == 0) { seg_s[nseg] = s; seg_e[nseg] = i; }
+            ++nseg;
+          }
+          s = -1;
+          cnt = 0;
+          continue;
         }
-        s = -1;
-        cnt = 0;
-        continue;
-      }
-      LaneVec x;
-      lane_load(x, states + (size_t)i * SEG_D, lane);
-      if (cnt == 0) {
-        curr = x;
-        curr_sq = xsq;
-        cnt = 1;
-        s = i;
-        continue;
-      }
-      const float xy = np_dot768(curr, x);
-      const float sim = __fdiv_rn(__fdiv_rn(xy, powf_half(curr_sq)), powf_half(xsq));   // scalar path: powf
-      if (sim >= thr_merge) {
-        const float fc = (float)cnt, fc1 = (float)(cnt + 1);
+        float x[SEG_PER_LANE];
+        lane_load_smem(x, ring[slot], lane);
+        // every lane holds its part of the row in registers before the async proxy may overwrite the slot
+        asm volatile("" ::"f"(x[0]), "f"(x[23]) : "memory");
+        __syncwarp();
+        prefetch(i + SEG_RING);
+        if (cnt == 0) {
 #pragma unroll
-        for (int k = 0; k < SEG_PER_LANE; ++k)
-          curr.v[k] = __fdiv_rn(__fadd_rn(__fmul_rn(curr.v[k], fc), x.v[k]), fc1);
-        curr_sq = __fadd_rn(np_dot768(curr, curr), 1e-8f);
-        cnt += 1;
-      } else {
-        curr = x;
-        curr_sq = xsq;
-        cnt += 1;   // not reset: reference quirk (segment_utils.py:103)
-        if (lane == 0) { seg_s[nseg] = s; seg_e[nseg] = i; mid_bd[nmid] = i; mid_seg[nmid] = nseg; }
-        ++nseg;
-        ++nmid;
-        s = i;
+          for (int k = 0; k < SEG_PER_LANE; ++k) curr[k] = x[k];
+          p_curr = px;
+          cnt = 1;
+          s = i;
+          continue;
+        }
+        // the decision ...
+        float a0 = __fmul_rn(curr[0], x[0]), a1 = __fmul_rn(curr[1], x[1]);
+#pragma unroll
+        for (int m = 1; m < 12; ++m) {
+          a0 = __fadd_rn(a0, __fmul_rn(curr[2 * m], x[2 * m]));
+          a1 = __fadd_rn(a1, __fmul_rn(curr[2 * m + 1], x[2 * m + 1]));
+        }
+        // ... and, speculatively, the merged centroid with its squared norm (independent of the decision)
+        const float fc = (float)cnt, fc1 = (float)(cnt + 1), rc1 = __frcp_rn(fc1);
+        float cand[SEG_PER_LANE];
+#pragma unroll
+        for (int k = 0; k < SEG_PER_LANE; ++k) cand[k] = div_by_count(__fadd_rn(__fmul_rn(curr[k], fc), x[k]), fc1, rc1);
+        float b0 = __fmul_rn(cand[0], cand[0]), b1 = __fmul_rn(cand[1], cand[1]);
+#pragma unroll
+        for (int m = 1; m < 12; ++m) {
+          b0 = __fadd_rn(b0, __fmul_rn(cand[2 * m], cand[2 * m]));
+          b1 = __fadd_rn(b1, __fmul_rn(cand[2 * m + 1], cand[2 * m + 1]));
+        }
+        float sxy = __fadd_rn(a0, a1), sqq = __fadd_rn(b0, b1);
+#pragma unroll
+        for (int o = 1; o <= 16; o <<= 1) {
+          sxy = __fadd_rn(sxy, __shfl_xor_sync(0xffffffffu, sxy, o));
+          sqq = __fadd_rn(sqq, __shfl_xor_sync(0xffffffffu, sqq, o));
+        }
+        const float xy = __fadd_rn(0.0f, sxy);
+        const float p_cand = powf_half(__fadd_rn(__fadd_rn(0.0f, sqq), 1e-8f));
+        const float sim = __fdiv_rn(__fdiv_rn(xy, p_curr), px);   // scalar path: powf denominators
+        cnt += 1;             // also after a split: reference quirk (segment_utils.py:103)
+        if (sim >= thr_merge) {
+#pragma unroll
+          for (int k = 0; k < SEG_PER_LANE; ++k) curr[k] = cand[k];
+          p_curr = p_cand;
+        } else {
+#pragma unroll
+          for (int k = 0; k < SEG_PER_LANE; ++k) curr[k] = x[k];
+          p_curr = px;
+          if (lane == 0) { seg_s[nseg] = s; seg_e[nseg] = i; mid_bd[nmid] = i; mid_seg[nmid] = nseg; }
+          ++nseg;
+          ++nmid;
+          s = i;
+        }
       }
     }
     if (s > -1) {

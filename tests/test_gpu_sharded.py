@@ -1,0 +1,95 @@
+"""The product-level sharded call (sylber_b200.distributed.segment_sharded) on real GPUs: the result of a list sharded
+over `world` ranks is BIT-IDENTICAL to one process calling `Segmenter(wav=list)` - uniform and mixed lengths
+(SURVEY.md 4 "sharded vs single-GPU result, bit-identical"; 8e: every rank pads to the global T_max).
+
+With >= world GPUs every rank owns one GPU and the segment table travels over NCCL; on a one-GPU box the ranks share
+cuda:0 and the table travels over gloo (NCCL refuses two ranks on one device) - the forward, the padding rule and the
+table packing are the same code either way."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _clips(kind):
+    g = torch.Generator().manual_seed(21)
+    if kind == "uniform":
+        return [torch.randn(1, 48000, generator=g) for _ in range(6)]
+    lens = [48000, 16000, 31234, 9000, 40000, 22222, 12000]
+    return [torch.randn(1, n, generator=g) for n in lens]
+
+
+def _worker(rank, world, port, kind, nccl, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dev = rank if nccl else 0
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl" if nccl else "gloo", rank=rank, world_size=world,
+                            **({"device_id": torch.device("cuda", dev)} if nccl else {}))
+    try:
+        from sylber_b200 import Segmenter, segment_sharded
+        from sylber_b200.distributed import shard_range
+        from sylber_b200.weights import syllabic_test_state_dict, SPEECH_LIKE_BIAS_NORM
+        seg = Segmenter(model_ckpt=None, state_dict=syllabic_test_state_dict(9, 0, SPEECH_LIKE_BIAS_NORM), device=f"cuda:{dev}")
+        clips = _clips(kind)
+        res_global = segment_sharded(seg, wav=clips, in_second=False, gather_features=True)
+        lo, hi = shard_range(len(clips), rank, world)
+        res_local = segment_sharded(seg, wav=clips[lo:hi], in_second=True, local_input=True)
+        q.put((rank, [(np.asarray(r["segments"]), r["segment_features"], r["hidden_states"]) for r in res_global],
+               [np.asarray(r["segments"]) for r in res_local]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind", ["uniform", "mixed"])
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_call_is_bit_identical_to_the_single_call(cuda, world, kind):
+    nccl = torch.cuda.device_count() >= world
+    if world == 4 and not nccl:
+        pytest.skip("world 4 runs with one GPU per rank only")
+    from sylber_b200 import Segmenter
+    from sylber_b200.distributed import shard_range
+    from sylber_b200.weights import syllabic_test_state_dict, SPEECH_LIKE_BIAS_NORM
+    clips = _clips(kind)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, kind, nccl, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = {}
+    for _ in range(world):
+        rank, res_global, res_local = q.get(timeout=600)
+        results[rank] = (res_global, res_local)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    single = Segmenter(model_ckpt=None, state_dict=syllabic_test_state_dict(9, 0, SPEECH_LIKE_BIAS_NORM), device="cuda:0")(
+        wav=clips, in_second=False)
+    assert sum(len(o["segments"]) for o in single) > 20          # the comparison is not vacuous
+    for rank, (res_global, res_local) in results.items():
+        lo, hi = shard_range(len(clips), rank, world)
+        assert len(res_global) == len(res_local) == len(clips)
+        for i, (seg, feat, hid) in enumerate(res_global):
+            want = np.asarray(single[i]["segments"])
+            assert seg.shape == want.shape and np.array_equal(seg, want), (rank, i)
+            assert np.array_equal(np.asarray(feat), np.asarray(single[i]["segment_features"])), (rank, i)   # gathered features
+            if lo <= i < hi:
+                assert np.array_equal(hid, single[i]["hidden_states"]), (rank, i)     # padded to the GLOBAL maximum
+            else:
+                assert hid is None
+            assert np.array_equal(res_local[i], want * 1.0 / 50 if len(want) else want)   # per-rank input lists, seconds
