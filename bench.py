@@ -2,18 +2,27 @@
 """Benchmark of the Segmenter forward path (BASELINE.json: audio frames/s on 10 s, 16 kHz clips).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--layers 9] [--mode parity]
+                    [--workload 10s|60s|mixed]
 
 One "step" = one pass of the hot path (conv front end -> 9-layer encoder -> segmentation -> segment pooling)
-over one batch of synthetic audio.  Workload at every N: BASELINE.json configs[1] per GPU - batch 32 x 10 s of
-N(0,1) "audio" (the distribution after the reference's (w-mean)/std), hubert-base architecture with the
-reference's 9 encoder layers, synthetic weights (no checkpoint exists offline).  Weak scaling: each rank owns
-32 utterances; the only collective is the all-gather of the fixed-stride segment table.
+over one batch of synthetic audio.  Workloads, per GPU (weak scaling, the rank's utterances are its own):
+  10s    BASELINE.json configs[1] / [2]: batch 32 x 10 s - the configuration the metric is quoted on (default)
+  60s    configs[3]: batch 8 x 60 s, T = 2999 - the attention-roofline case
+  mixed  configs[4]: 64 clips of 2-30 s (lengths torch.randint(32000, 480001, seed 2)), zero padded to
+         the GLOBAL maximum over all ranks' clips - the T_max one process calling the reference on the whole list
+         would use (sylber.py:93-118; results depend on it).  frames/s counts VALID frames.
+Audio is N(0,1) (the distribution after the reference's (w-mean)/std); hubert-base architecture with the reference's 9
+encoder layers, synthetic weights with speech-like segment occupancy (weights.SPEECH_LIKE_BIAS_NORM; no checkpoint
+exists offline; SYLBER_CKPT=<path> uses a real one).
 
 JSON line (rank 0): value = frames/s with inputs resident in HBM (CUDA events, max over ranks);
-e2e = the same through Segmenter.__call__ from host tensors (H2D + D2H inside the timed region);
-roofline = dominant stage against MEASURED_PEAKS.json; stages = per-stage device time and achieved rates;
-cpu_baseline = the CPU oracle port (torch CPU ops + NumPy segmentation, what the reference executes) on this
-box's host cores.  `--impl reference` times that CPU path alone.
+e2e = the same through the public call (Segmenter.__call__, or segment_sharded with its all-gather at N > 1) from
+pinned host tensors to NumPy results; roofline = the dominant kernel (gemm3_tc_kernel) TIME-WEIGHTED over all its
+launches against MEASURED_PEAKS.json, with the best launch, the attention+MLP path (LayerNorms included) and the
+whole step as sub-fields; stages = per-stage device time and achieved rates; cpu_baseline = the reference's own CPU
+implementation (oracle/_ref, the unmodified sylber.Segmenter) on this box's host cores, which also yields
+config.segment_agreement (device segments vs the reference's on the same clips).
+`--impl reference` times that CPU path alone on the same clips.
 """
 from __future__ import annotations
 
@@ -34,11 +43,13 @@ import torch  # noqa: E402
 
 METRIC = "audio frames/sec (16 kHz, 10 s clips)"
 UNIT = "frames/s"
-N_SAMPLES = 160000
-BATCH_PER_GPU = 32
 THR_NORM, THR_MERGE = 2.6, 0.8
 CONV_K = (10, 3, 3, 3, 3, 2, 2)
 CONV_S = (5, 2, 2, 2, 2, 2, 2)
+MODE_ERR = {"parity": "conv4-6 and the feature projection run split hi/lo f16 = 3 passes; 4.1e-4 rel vs fp32",
+            "strict": "conv1-6, projection, pos-conv split; 3.0e-4", "exact": "every GEMM split; 2.5e-5",
+            "fast": "no split; 5.1e-4"}
+SPLIT_CONV = {"fast": (), "parity": (4, 5, 6), "strict": (1, 2, 3, 4, 5, 6), "exact": (1, 2, 3, 4, 5, 6)}
 
 
 def conv_lengths(n):
@@ -67,6 +78,10 @@ def stage_flops(n_samples, layers):
     }, T, L
 
 
+GEMM_STAGES = ("conv1_gemm", "conv2_6_gemm", "feature_proj_gemm", "qkv_gemm", "out_proj_gemm", "ffn1_gemm", "ffn2_gemm")
+ENC_STAGES = ("qkv_gemm", "attention", "out_proj_gemm", "ffn1_gemm", "ffn2_gemm")
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -77,7 +92,7 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed regions."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -123,54 +138,137 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU path (oracle port): what the reference executes, restated so it can run on the GPU box
+# workload
 # --------------------------------------------------------------------------------------------------
-def cpu_step(sd, wav, lens, layers):
-    from oracle.hubert_ref import hubert_forward
-    from oracle import segment_ref
-    hidden = hubert_forward(sd, wav, lens, layers).numpy()
-    outs = []
-    for states in hidden:
-        seg = segment_ref.get_segment(states, THR_NORM, THR_MERGE)
-        outs.append(segment_ref.package(states, seg, in_second=True))
-    return outs
+def make_workload(name, world, rank, pin=True):
+    """(list of this rank's (1, n) fp32 clips, padded length of the call, description).  Deterministic in (name, world)."""
+    pin = pin and torch.cuda.is_available()
+    if name in ("10s", "60s"):
+        n, B = (160000, 32) if name == "10s" else (960000, 8)
+        g = torch.Generator().manual_seed(1)
+        if world * B <= 256:
+            wav = torch.randn(B * world, n, generator=g)[rank * B:(rank + 1) * B].contiguous()
+        else:
+            wav = torch.randn(B, n, generator=torch.Generator().manual_seed(1 + rank))
+        wav = wav.pin_memory() if pin else wav       # e2e inputs start in pinned host memory
+        return [wav[i:i + 1] for i in range(B)], n, f"batch={B} synthetic {n // 16000} s 16 kHz wav per GPU"
+    B = 64
+    lens = torch.randint(32000, 480001, (B * world,), generator=torch.Generator().manual_seed(2)).tolist()
+    g = torch.Generator().manual_seed(1 + rank)
+    mine = lens[rank * B:(rank + 1) * B]
+    clips = [torch.randn(1, n, generator=g) for n in mine]
+    clips = [c.pin_memory() for c in clips] if pin else clips
+    return clips, max(lens), (f"{B} clips of 2-30 s per GPU (lengths torch.randint(32000, 480001, ({B * world},), seed 2)), every "
+                              f"clip zero padded to the GLOBAL maximum over all ranks ({max(lens)} samples) = the reference's "
+                              f"padding semantics for one call on the whole list")
 
 
-def time_cpu(sd, layers, batch, steps, warmup, seed=1):
-    torch.set_num_threads(os.cpu_count())
-    g = torch.Generator().manual_seed(seed)
-    wav = torch.randn(batch, N_SAMPLES, generator=g)
-    lens = [N_SAMPLES] * batch
-    T = conv_lengths(N_SAMPLES)[6]
-    for _ in range(warmup):
-        cpu_step(sd, wav, lens, layers)
-    times = []
-    for _ in range(steps):
+def load_weights(layers):
+    from sylber_b200.weights import syllabic_test_state_dict, normalize_state_dict, SPEECH_LIKE_BIAS_NORM
+    ckpt = os.environ.get("SYLBER_CKPT")
+    if ckpt:
+        return normalize_state_dict(torch.load(ckpt, map_location="cpu")), f"checkpoint {ckpt}"
+    return syllabic_test_state_dict(layers, 0, bias_norm=SPEECH_LIKE_BIAS_NORM), "synthetic"
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU path: the unmodified reference from oracle/_ref when it is installed, else the oracle port
+# --------------------------------------------------------------------------------------------------
+class CpuPath:
+    def __init__(self, sd, layers):
+        from oracle import make_ref
+        torch.set_num_threads(os.cpu_count())
+        self.sd, self.layers = sd, layers
+        self.kind = "reference" if make_ref.available() else "port"
+        if self.kind == "reference":
+            self.seg = make_ref.reference_segmenter(sd, layers)
+            _, self.get_segment = make_ref.load_reference()
+        else:
+            from oracle import segment_ref
+            self.get_segment = segment_ref.get_segment
+
+    def full(self, clips):
+        """What the user of the reference runs: Segmenter.__call__(wav=list) -> list of dicts."""
+        if self.kind == "reference":
+            return self.seg(wav=clips, in_second=False)
+        from oracle.hubert_ref import hubert_forward
+        from oracle import segment_ref
+        lens = [c.shape[1] for c in clips]
+        batch = torch.zeros(len(clips), max(lens))
+        for i, c in enumerate(clips):
+            batch[i, :lens[i]] = c[0]
+        hidden = hubert_forward(self.sd, batch, lens, self.layers).numpy()
+        return [segment_ref.package(st, segment_ref.get_segment(st, THR_NORM, THR_MERGE), in_second=False) for st in hidden]
+
+    def split(self, clips):
+        """(model-only ms, segmentation-only ms) of one pass: the HubertModel forward and the get_segment loop apart."""
+        lens = [c.shape[1] for c in clips]
+        batch = torch.zeros(len(clips), max(lens))
+        mask = torch.zeros(len(clips), max(lens), dtype=torch.long)
+        for i, c in enumerate(clips):
+            batch[i, :lens[i]] = c[0]
+            mask[i, :lens[i]] = 1
         t0 = time.perf_counter()
-        cpu_step(sd, wav, lens, layers)
-        times.append(time.perf_counter() - t0)
-    total = sum(times)
-    return batch * T * steps / total, total / steps * 1e3
+        with torch.no_grad():
+            if self.kind == "reference":
+                hidden = self.seg.speech_model(batch, attention_mask=mask).last_hidden_state.numpy()
+            else:
+                from oracle.hubert_ref import hubert_forward
+                hidden = hubert_forward(self.sd, batch, lens, self.layers).numpy()
+        t1 = time.perf_counter()
+        for st in hidden:
+            self.get_segment(st, THR_NORM, THR_MERGE)
+        t2 = time.perf_counter()
+        return (t1 - t0) * 1e3, (t2 - t1) * 1e3
+
+    def describe(self):
+        return ("unmodified sylber.Segmenter from oracle/_ref (pip-installed copy of the reference; HubertModel of the installed "
+                "transformers, NumPy get_segment), device='cpu'" if self.kind == "reference" else
+                "oracle/ port (torch CPU fp32 ops + NumPy get_segment restatement)")
+
+
+def cpu_sample(name, clips):
+    """Bounded sample of the rank's clips the CPU path is timed on (the whole batch where that is a few seconds)."""
+    if name == "10s":
+        return clips, f"all {len(clips)} clips of the step"
+    if name == "60s":
+        return clips[:4], "4 of the step's 8 clips"
+    return clips[:16], "the first 16 of the step's 64 clips, padded to their own maximum (reference list call)"
+
+
+def valid_frames(clips):
+    return sum(conv_lengths(c.shape[1])[6] for c in clips)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from sylber_b200.weights import syllabic_test_state_dict, SPEECH_LIKE_BIAS_NORM
-    sd = syllabic_test_state_dict(args.layers, 0, bias_norm=SPEECH_LIKE_BIAS_NORM)
-    batch = 4 if N_SAMPLES <= 160000 else 1
-    fps, ms = time_cpu(sd, args.layers, batch, args.steps, args.warmup)
+    sd, wsrc = load_weights(args.layers)
+    clips, pad_to, desc = make_workload(args.workload, 1, 0, pin=False)
+    sample, sample_desc = cpu_sample(args.workload, clips)
+    cpu = CpuPath(sd, args.layers)
+    frames = valid_frames(sample)
+    for _ in range(max(args.warmup, 0)):
+        cpu.full(sample)
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        cpu.full(sample)
+        times.append(time.perf_counter() - t0)
+    ms = sum(times) / len(times) * 1e3
+    fps = frames / (ms / 1e3)
+    model_ms, seg_ms = cpu.split(sample)
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"batch={BATCH_PER_GPU} synthetic {N_SAMPLES // 16000} s 16 kHz wav, sylber_base ({args.layers}L/768d)",
-                   "note": "CPU path of the reference restated in oracle/ (torch CPU conv/linear/SDPA-equivalent ops + "
-                           "NumPy get_segment); each step is a bounded sample of 4 clips of the workload"},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{batch} x {N_SAMPLES // 16000} s clips per step, {args.steps} steps, torch {torch.__version__} fp32, "
-                                   f"os.cpu_count()={os.cpu_count()}"},
+        "config": {"workload": f"{desc}, sylber_base ({args.layers}L/768d)", "weights": wsrc,
+                   "note": f"CPU arm: {cpu.describe()}; each step = Segmenter.__call__ on {sample_desc}"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": cpu.kind,
+                         "sample": f"{sample_desc} ({frames} valid frames per step), {args.steps} steps, torch {torch.__version__} fp32, "
+                                   f"os.cpu_count()={os.cpu_count()}",
+                         "split_ms": {"model_only": round(model_ms, 1), "segmentation_only": round(seg_ms, 1), "full": round(ms, 1)}},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -178,12 +276,46 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------
+# the PyTorch-eager library bar on the same GPU: transformers.HubertModel, model forward only
+# --------------------------------------------------------------------------------------------------
+def library_baseline(sd, layers, wav_dev, T, reps=3):
+    try:
+        from transformers import HubertConfig, HubertModel
+        model = HubertModel(HubertConfig(num_hidden_layers=layers))
+        model.load_state_dict(sd, strict=False)
+        model = model.eval().to(wav_dev.device)
+        out = {}
+        for name, ctx, tf32 in (("fp32", None, False), ("tf32", None, True), ("bf16_autocast", torch.bfloat16, False)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            with torch.no_grad(), torch.autocast("cuda", dtype=ctx, enabled=ctx is not None):
+                model(wav_dev)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    model(wav_dev)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            out[name] = {"ms_per_forward": round(ms, 2), "frames_per_s": round(wav_dev.shape[0] * T / (ms / 1e3))}
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        del model
+        torch.cuda.empty_cache()
+        out["what"] = ("transformers.HubertModel eager on this GPU (cuDNN convs, cuBLAS linears, SDPA), model forward only - no "
+                       "segmentation / pooling; fp32 is what the reference runs with device='cuda'")
+        return out
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": repr(e)[:200]}
+
+
+# --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch.distributed as dist
-    from sylber_b200 import Segmenter
-    from sylber_b200.weights import syllabic_test_state_dict, SPEECH_LIKE_BIAS_NORM
+    from sylber_b200 import Segmenter, segment_sharded
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -198,35 +330,61 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     layers = args.layers
-    sd = syllabic_test_state_dict(layers, 0, bias_norm=SPEECH_LIKE_BIAS_NORM)
+    sd, wsrc = load_weights(layers)
+    clips, pad_to, desc = make_workload(args.workload, world, rank)
+    B = len(clips)
+    max_batch = 32
     seg = Segmenter(model_ckpt=None, state_dict=sd, encoding_layer=layers, device=f"cuda:{local}", mode=args.mode,
-                    max_batch=BATCH_PER_GPU, **({"streams": args.streams} if args.streams else {}))
+                    max_batch=max_batch, **({"streams": args.streams} if args.streams else {}))
     eng = seg._engine
-    B = BATCH_PER_GPU
-    flops, T, L = stage_flops(N_SAMPLES, layers)
-    g = torch.Generator().manual_seed(1)
-    wav_all = torch.randn(B * world, N_SAMPLES, generator=g) if world * B <= 256 else None
-    wav_host = wav_all[rank * B:(rank + 1) * B].contiguous().pin_memory()   # e2e inputs start in pinned host memory
-    wav_dev = wav_host.to(dev)
-    n_dev = torch.full((B,), N_SAMPLES, dtype=torch.int32, device=dev)
+    lens = [c.shape[1] for c in clips]
+    flops, T, L = stage_flops(pad_to, layers)           # executed work: every clip is padded to pad_to
+    frames_valid_local = valid_frames(clips)
     thr_n, thr_m = np.float32(THR_NORM), np.float32(THR_MERGE)
-    gathered_cnt = torch.empty((world * B,), dtype=torch.int32, device=dev) if world > 1 else None
-    gathered_seg = torch.empty((world * B, T, 2), dtype=torch.int32, device=dev) if world > 1 else None
+
+    # device-resident inputs: sub-batches of <= max_batch rows, each with its own workspace / output slot
+    subs = []
+    for lo in range(0, B, max_batch):
+        hi = min(lo + max_batch, B)
+        wav_dev = torch.zeros(hi - lo, pad_to, device=dev)
+        for i in range(lo, hi):
+            wav_dev[i - lo, :lens[i]] = clips[i][0].to(dev)
+        n_dev = torch.tensor(lens[lo:hi], dtype=torch.int32, device=dev)
+        subs.append((wav_dev, n_dev))
+    per_rank = B
+    gathered_cnt = torch.empty((world * per_rank,), dtype=torch.int32, device=dev) if world > 1 else None
+    gathered_seg = torch.empty((world * per_rank, T, 2), dtype=torch.int32, device=dev) if world > 1 else None
 
     run_stream = torch.cuda.Stream(device=dev)      # a real stream: the library replays its CUDA graph on it
     torch.cuda.set_stream(run_stream)
 
     def step():
-        hidden, sg, cnt, feat = eng.forward(wav_dev, n_dev, thr_n, thr_m)
+        outs = [eng.forward(w, n, thr_n, thr_m, slot=("bench", k)) for k, (w, n) in enumerate(subs)]
         if world > 1:  # the one exchange of the path: the fixed-stride segment table
+            cnt = torch.cat([o[2] for o in outs]) if len(outs) > 1 else outs[0][2]
+            sg = torch.cat([o[1] for o in outs]) if len(outs) > 1 else outs[0][1]
             dist.all_gather_into_tensor(gathered_cnt, cnt)
             dist.all_gather_into_tensor(gathered_seg, sg)
-        return hidden, sg, cnt, feat
+        return outs
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    frames_valid = sum_over_ranks(frames_valid_local)
 
     # ---------------- device-resident timing (value) ----------------
     for _ in range(max(args.warmup, 3)):
@@ -242,7 +400,7 @@ def run_ours(args):
         out = step()
     e1.record()
     barrier()
-    ms_total = e0.elapsed_time(e1)
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
     # per-stage device time: the same K steps again with the library's stage events enabled (eager launches instead
     # of the CUDA-graph replay used above, because events cannot be read back from inside a graph)
     eng.profile(True)
@@ -257,32 +415,28 @@ def run_ours(args):
     ms_prof_total = p0.elapsed_time(p1)
     prof = eng.profile_read()
     eng.profile(False)
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    frames_per_step = world * B * T
-    value = frames_per_step * args.steps / (ms_total / 1e3)
-    seg_counts = out[2].cpu().numpy()
+    value = frames_valid * args.steps / (ms_total / 1e3)
+    seg_counts = torch.cat([o[2] for o in out]).cpu().numpy()
 
-    # ---------------- end-to-end through Segmenter.__call__ from host tensors ----------------
-    wav_list = [wav_host[i:i + 1] for i in range(B)]
+    # ---------------- end-to-end through the public call, from pinned host tensors to NumPy results ----------------
+    def e2e_call():
+        if world > 1:   # product-level sharded call: local forward + all-gather of the segment table on every step
+            return segment_sharded(seg, wav=clips, in_second=True, local_input=True, pad_to=pad_to)
+        return seg(wav=clips, in_second=True, pad_to=pad_to)
+
     for _ in range(3):
-        res = seg(wav=wav_list, in_second=True)
+        res = e2e_call()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = seg(wav=wav_list, in_second=True)
+        res = e2e_call()
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = frames_per_step * args.steps / float(t.item())
-    h2d = B * N_SAMPLES * 4 + B * 4
-    d2h = B * T * 768 * 4 + B * 4 + sum(int(np.asarray(r["segments"]).size) * 4 + int(np.asarray(r["segment_features"]).size) * 4
-                                        for r in res)
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_value = frames_valid * args.steps / e2e_s
+    mine = res[rank * B:(rank + 1) * B] if world > 1 else res
+    h2d = sum(lens) * 4 + B * 4
+    d2h = B * T * 768 * 4 + B * 4 + B * T * 2 * 4 + sum(int(np.asarray(r["segment_features"]).size) * 4 for r in mine)
 
     if rank != 0:
         if world > 1:
@@ -296,77 +450,97 @@ def run_ours(args):
         if cnt == 0:
             continue
         ms_step = ms / args.steps
-        entry = {"ms_per_step": round(ms_step, 4), "share": round(ms / ms_prof_total, 4)}
+        entry = {"ms_per_step": round(ms_step, 4), "share": round(ms / ms_prof_total, 4), "launch_regions": cnt // args.steps}
         if name in flops and name != "conv0_gn_gelu":
             tf = flops[name] * B / (ms_step * 1e-3) / 1e12
             entry.update({"bound": "tensor", "achieved_tflops": round(tf, 1), "frac": round(tf / peaks["tf_sustained"], 4)})
         stages[name] = entry
-    # HBM-bound stages: algorithmic bytes
+    M = B * T
     if "conv0_gn_gelu" in stages:
         n_out = 2 if args.mode in ("strict", "exact") else 1     # fp16 hi (+ lo only when conv1 runs split)
-        by = B * (2 * N_SAMPLES * 4 + L[0] * 512 * 2 * n_out)   # wav read twice (stats + apply), fp16 activation written
+        by = B * (2 * pad_to * 4 + L[0] * 512 * 2 * n_out)       # wav read twice (stats + apply), fp16 activation written
         gbs = by / (stages["conv0_gn_gelu"]["ms_per_step"] * 1e-3) / 1e9
         stages["conv0_gn_gelu"].update({"bound": "hbm", "achieved_gbs": round(gbs, 1), "frac": round(gbs / peaks["hbm_gbs"], 4)})
-    if "layernorm" in stages:
-        M = B * T
-        # LN(512): fp32 in, fp16 hi (+ lo) out; LN(768): fp32 GEMM output + residual (fp16 hi + lo pair; fp32 for the
-        # post-pos-conv one) in, fp16 pair out; the last one also writes the fp32 hidden states
-        by = M * 512 * (4 + (4 if args.mode != "fast" else 2)) + (1 + 2 * layers) * M * 768 * (4 + 4 + 4) + M * 768 * 4
+    if "layernorm" in stages:    # LN(512): fp32 in, fp16 hi (+ lo) out; LN(768) after the positional conv: two fp32 in, fp16 pair out
+        by = M * 512 * (4 + (4 if args.mode != "fast" else 2)) + M * 768 * (4 + 4 + 4)
         gbs = by / (stages["layernorm"]["ms_per_step"] * 1e-3) / 1e9
         stages["layernorm"].update({"bound": "hbm", "achieved_gbs": round(gbs, 1), "frac": round(gbs / peaks["hbm_gbs"], 4)})
+    if "layernorm_encoder" in stages:   # fp32 GEMM output + residual pair in, pair out; the last one also writes fp32 hidden
+        by = 2 * layers * M * 768 * (4 + 4 + 4) + M * 768 * 4
+        gbs = by / (stages["layernorm_encoder"]["ms_per_step"] * 1e-3) / 1e9
+        stages["layernorm_encoder"].update({"bound": "hbm", "achieved_gbs": round(gbs, 1), "frac": round(gbs / peaks["hbm_gbs"], 4)})
     if "attention" in stages:
         by = layers * B * 4 * T * 768 * 2
         stages["attention"]["hbm_gbs"] = round(by / (stages["attention"]["ms_per_step"] * 1e-3) / 1e9, 1)
         stages["attention"]["hbm_frac"] = round(stages["attention"]["hbm_gbs"] / peaks["hbm_gbs"], 4)
-    enc = ["qkv_gemm", "attention", "out_proj_gemm", "ffn1_gemm", "ffn2_gemm"]
-    enc_ms = sum(stages[s]["ms_per_step"] for s in enc if s in stages)
-    enc_tf = sum(flops[s] for s in enc) * B / (enc_ms * 1e-3) / 1e12 if enc_ms else 0.0
-    # Dominant kernel = gemm3_tc_kernel (63 % of device time, profiles/r02_ncu_summary.md); its largest single launch is conv1 (M = 32 x 15999, N = 512, K = 1536,
-    # one pass in the default mode), which has its own stage timer so that `achieved` is a per-launch figure.
-    dom = "conv1_gemm"
-    traffic = None
+
+    def tf_of(names, extra_ms=0.0):
+        ms = sum(stages[s]["ms_per_step"] for s in names if s in stages) + extra_ms
+        fl = sum(flops[s] for s in names if s in flops) * B
+        return (fl / (ms * 1e-3) / 1e12 if ms else 0.0), ms, fl
+
+    # Dominant kernel = gemm3_tc_kernel: conv1-6 (implicit GEMM), feature projection, QKV, out-projection, FFN1, FFN2 -
+    # 7 + 4 * layers launches per step.  `achieved` is TIME-WEIGHTED over all of them (sum of algorithmic FLOPs / sum of
+    # their device time); the best single launch (conv1, which has its own stage timer) is a sub-field.
+    dom_tf, dom_ms, dom_fl = tf_of(GEMM_STAGES)
+    n_launch = 7 + 4 * layers
+    traffic = alg_bytes = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("gemm3_tc_kernel.conv1", {}).get("dram_bytes_per_launch")
-    conv_ms = stages["conv1_gemm"]["ms_per_step"] + stages["conv2_6_gemm"]["ms_per_step"]
-    # tensor-core work actually issued by the conv stack: split sites run 3 passes (mode presets: include/sylber_b200.h)
+    tsrc = None
+    if os.path.exists(tpath) and args.workload == "10s" and args.mode == "parity" and layers == 9:
+        tj = json.load(open(tpath))
+        ent = tj.get("gemm3_tc_kernel.all_launches") or {}
+        traffic, alg_bytes, tsrc = ent.get("dram_bytes_per_launch_mean"), ent.get("algorithmic_bytes_per_launch_mean"), ent.get("source")
+    enc_tf, enc_ms, _ = tf_of(ENC_STAGES)
+    enc_ln_ms = stages.get("layernorm_encoder", {}).get("ms_per_step", 0.0)
+    encln_tf, encln_ms, _ = tf_of(ENC_STAGES, enc_ln_ms)
+    step_ms = ms_total / args.steps
+    all_fl = sum(flops.values()) * B
+    step_tf = all_fl / (step_ms * 1e-3) / 1e12
     per_layer = [2 * 512 * 512 * k * L[i] for i, k in zip(range(1, 7), (3, 3, 3, 3, 2, 2))]
-    split_layers = {"fast": (), "parity": (4, 5, 6), "strict": (1, 2, 3, 4, 5, 6), "exact": (1, 2, 3, 4, 5, 6)}[args.mode]
-    conv_eq = sum(f * (3 if i in split_layers else 1) for i, f in zip(range(1, 7), per_layer)) * B / (conv_ms * 1e-3) / 1e12
+    conv_ms = stages["conv1_gemm"]["ms_per_step"] + stages["conv2_6_gemm"]["ms_per_step"]
+    conv_eq = sum(f * (3 if i in SPLIT_CONV[args.mode] else 1) for i, f in zip(range(1, 7), per_layer)) * B / (conv_ms * 1e-3) / 1e12
     roofline = {
-        "bound": "tensor", "kernel": "gemm3_tc_kernel", "launch": f"conv1 implicit GEMM, M={B}x{L[1]} N=512 K=1536", "stage": dom,
-        "achieved": stages[dom]["achieved_tflops"], "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-        "frac": stages[dom]["frac"], "traffic": traffic,
+        "bound": "tensor", "kernel": "gemm3_tc_kernel",
+        "launch": f"time-weighted over all {n_launch} launches per step (conv1-6, feature projection, QKV, out-proj, FFN1, FFN2)",
+        "achieved": round(dom_tf, 1), "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": round(dom_tf / peaks["tf_sustained"], 4),
+        "traffic": traffic,
         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); fp16 and bf16 share the tensor rate",
-        "algorithmic_flops_per_launch": flops[dom] * B,
-        # A = conv0 activation (fp16 hi) read once, output fp16 hi (+ lo only when conv2 runs split), weights once
-        "algorithmic_bytes_per_launch": B * (L[0] * 512 * 2 + L[1] * 512 * 2 * (2 if args.mode in ("strict", "exact") else 1)) + 512 * 1536 * 2,
-        "traffic_source": "profiles/ncu_traffic.json (ncu --set full dram bytes of the same launch, parity mode)",
+        "algorithmic_flops_per_launch": dom_fl / n_launch, "launches_per_step": n_launch,
+        "kernel_ms_per_step": round(dom_ms, 4), "kernel_share_of_step": round(dom_ms / (ms_prof_total / args.steps), 4),
+        "algorithmic_bytes_per_launch": alg_bytes, "traffic_source": tsrc,
+        "best_launch": {"launch": f"conv1 implicit GEMM, M={B}x{L[1]} N=512 K=1536", "achieved": stages["conv1_gemm"]["achieved_tflops"],
+                        "frac": stages["conv1_gemm"]["frac"], "ms": stages["conv1_gemm"]["ms_per_step"]},
+        "per_stage_frac": {s: stages[s]["frac"] for s in GEMM_STAGES if s in stages},
         "conv_stack_tensor_work": {"achieved_incl_split_passes": round(conv_eq, 1), "unit": "TFLOP/s issued to the tensor cores",
                                    "frac": round(conv_eq / peaks["tf_sustained"], 4), "ms_per_step": round(conv_ms, 4)},
-        "attn_mlp_path": {"achieved": round(enc_tf, 1), "frac": round(enc_tf / peaks["tf_sustained"], 4), "unit": "TFLOP/s",
-                          "ms_per_step": round(enc_ms, 4)},
+        "attn_mlp_path": {"achieved": round(encln_tf, 1), "frac": round(encln_tf / peaks["tf_sustained"], 4), "unit": "TFLOP/s",
+                          "ms_per_step": round(encln_ms, 4),
+                          "what": "QKV + attention + out-proj + FFN1 + FFN2 + the two LayerNorms of every encoder layer",
+                          "without_layernorms": {"achieved": round(enc_tf, 1), "frac": round(enc_tf / peaks["tf_sustained"], 4),
+                                                 "ms_per_step": round(enc_ms, 4)}},
+        "step": {"achieved": round(step_tf, 1), "frac": round(step_tf / peaks["tf_sustained"], 4), "unit": "TFLOP/s",
+                 "what": "all algorithmic FLOPs of the step / device-resident step time (segmentation, LayerNorms, conv0 included in the time)"},
         "attention_hbm": {"achieved": stages.get("attention", {}).get("hbm_gbs"), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                           "frac": stages.get("attention", {}).get("hbm_frac")},
     }
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16 tensor-core operands, f32 accumulate/LayerNorm/softmax/residual; mode=" + args.mode +
-                 {"parity": " (conv4-6 and the feature projection run split hi/lo f16 = 3 passes; 4.4e-4 rel vs fp32)",
-                  "strict": " (conv1-6, projection, pos-conv split; 3.0e-4)", "exact": " (every GEMM split; 2.7e-5)",
-                  "fast": " (no split; 5.5e-4)"}[args.mode],
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": f"f16 tensor-core operands, f32 accumulate/LayerNorm/softmax/residual; mode={args.mode} ({MODE_ERR[args.mode]})",
         "data": "synthetic",
-        "config": {"workload": f"batch={B} synthetic {N_SAMPLES // 16000} s 16 kHz wav per GPU, sylber_base ({layers}L/768d), 1xB200 per rank",
-                   "frames_per_clip": T, "batch_per_gpu": B, "mode": args.mode, "parallelism": f"dp{world} by utterance",
+        "config": {"workload": f"{desc}, sylber_base ({layers}L/768d), 1xB200 per rank", "weights": wsrc,
+                   "frames_padded_per_clip": T, "clips_per_gpu": B, "valid_frames_per_step": int(frames_valid),
+                   "padded_frames_per_step": int(world * B * T), "t_max_definition": "global maximum over all ranks' clips",
+                   "mode": args.mode, "parallelism": f"dp{world} by utterance",
                    "l2": "per-step working set (~4 GB of activations) exceeds the 126 MB L2; no explicit flush",
                    "segments_per_clip_mean": float(seg_counts.mean()),
-                   "e2e_input": f"list of {B} (1, {N_SAMPLES}) fp32 views of one pinned host tensor",
-                   "variant_env": {k: v for k, v in os.environ.items() if k.startswith("SYL_")}},
+                   "e2e_input": f"list of {B} (1, n) fp32 views of pinned host memory"
+                                + ("; e2e = segment_sharded(local_input=True): forward + all-gather of counts and segment table" if world > 1 else "")},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / args.steps * 1e3},
-        "gpu_launches": eng.launch_count(True) * args.steps,
+        "gpu_launches": eng.launch_count(True) * len(subs) * args.steps,
         "clocks": clocks,
         "roofline": roofline,
         "stages": stages,
@@ -375,11 +549,35 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu:
         torch.cuda.synchronize()
-        n_cpu = 8 if N_SAMPLES <= 160000 else 2
-        fps, ms = time_cpu(sd, layers, n_cpu, 2, 1)
-        line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"{n_cpu} x {N_SAMPLES // 16000} s clips, 1 warm-up + 2 timed passes of oracle/ (torch CPU fp32 + NumPy "
-                                          f"get_segment), os.cpu_count()={os.cpu_count()}", "ms_per_step": ms}
+        from oracle import agreement as A
+        cpu = CpuPath(sd, layers)
+        sample, sample_desc = cpu_sample(args.workload, clips)
+        n_s = len(sample)
+        ours = seg(wav=sample, in_second=False)            # the device result on exactly the clips the CPU path sees
+        cpu.full(sample)
+        times = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            ref = cpu.full(sample)
+            times.append(time.perf_counter() - t0)
+        ms = sum(times) / len(times) * 1e3
+        model_ms, seg_ms = cpu.split(sample)
+        line["cpu_baseline"] = {"value": valid_frames(sample) / (ms / 1e3), "unit": UNIT, "cores": torch.get_num_threads(), "kind": cpu.kind,
+                                "sample": f"{sample_desc}: 1 warm-up + 2 timed passes of {cpu.describe()}, os.cpu_count()={os.cpu_count()}",
+                                "ms_per_step": ms,
+                                "split_ms": {"model_only": round(model_ms, 1), "segmentation_only": round(seg_ms, 1), "full": round(ms, 1)}}
+        recs = [A.compare_utterance(ref[i]["hidden_states"], ours[i]["hidden_states"], ours[i]["segments"], THR_NORM, THR_MERGE)
+                for i in range(n_s)]
+        summ = A.summarize(recs)
+        line["config"]["segment_agreement"] = {
+            "clips_with_identical_segments": summ["agree"], "clips": n_s, "mode": args.mode,
+            "all_differences_explained_by_margin_below_state_error": summ["all_flips_explained"],
+            "hidden_rel_err_max": summ["rel_max"], "min_margin": summ["min_margin"],
+            "flips": [{k: f[k] for k in ("utterance", "kind", "frame", "margin", "delta")} for f in summ["flips"]],
+            "note": "device segments vs the CPU reference's on the same clips; get_segment thresholds fp32 norms / cosines, so a clip "
+                    "differs exactly when one of its decisions sits closer to the threshold than the state error (oracle/agreement.py)"}
+    if world == 1 and args.library_baseline:
+        line["gpu_library_baseline"] = library_baseline(sd, layers, subs[0][0], T)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -393,15 +591,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", type=int, default=9)
     ap.add_argument("--mode", default="parity", choices=["parity", "strict", "fast", "exact"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / segment_agreement leg")
+    ap.add_argument("--library-baseline", action="store_true", help="also time transformers.HubertModel eager on the GPU")
     ap.add_argument("--streams", type=int, default=0, help="sub-batches in flight in the e2e leg (0 = Segmenter default)")
-    ap.add_argument("--workload", default="10s", choices=["10s", "60s"],
+    ap.add_argument("--workload", default="10s", choices=["10s", "60s", "mixed"],
                     help="10s = BASELINE configs[1]/[2] (batch 32 x 10 s per GPU, the metric's configuration); "
-                         "60s = configs[3] (batch 8 x 60 s, T = 2999: the attention-roofline case)")
+                         "60s = configs[3] (batch 8 x 60 s, T = 2999); mixed = configs[4] (64 clips of 2-30 s per GPU)")
     args = ap.parse_args()
-    global N_SAMPLES, BATCH_PER_GPU
-    if args.workload == "60s":
-        N_SAMPLES, BATCH_PER_GPU = 960000, 8
     if args.impl == "reference":
         run_reference(args)
     else:

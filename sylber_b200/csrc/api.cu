@@ -44,9 +44,9 @@ constexpr int kPosCg = 48;     // channels per group
 std::string g_create_error;
 
 // device-time profiling by stage (CUDA events on the launch stream, enabled by syl_profile_enable)
-enum Stage { ST_CONV0 = 0, ST_CONV, ST_LN, ST_PROJ, ST_POS, ST_QKV, ST_ATTN, ST_OUT, ST_FFN1, ST_FFN2, ST_SEG, ST_CONV1, ST_COUNT };
+enum Stage { ST_CONV0 = 0, ST_CONV, ST_LN, ST_PROJ, ST_POS, ST_QKV, ST_ATTN, ST_OUT, ST_FFN1, ST_FFN2, ST_SEG, ST_CONV1, ST_LN_ENC, ST_COUNT };
 const char* const kStageNames[ST_COUNT] = {"conv0_gn_gelu", "conv2_6_gemm", "layernorm", "feature_proj_gemm", "pos_conv_gemm",
-                                           "qkv_gemm", "attention", "out_proj_gemm", "ffn1_gemm", "ffn2_gemm", "segment_pool", "conv1_gemm"};
+                                           "qkv_gemm", "attention", "out_proj_gemm", "ffn1_gemm", "ffn2_gemm", "segment_pool", "conv1_gemm", "layernorm_encoder"};
 struct ProfRec {
   int stage;
   cudaEvent_t a, b;
@@ -900,7 +900,7 @@ int run_layer(syl_handle* h, int l, float* h_out, cudaStream_t st) {
     if ((rc = launch_gemm(h, pl.out[l], st, h->sm_count))) return rc;
   }
   {
-    StageTimer tm(h, ST_LN, st);   // h = LN(h + attn); the residual stream is the fp16 pair (h16_hi, h16_lo), in place
+    StageTimer tm(h, ST_LN_ENC, st);   // h = LN(h + attn); the residual stream is the fp16 pair (h16_hi, h16_lo), in place
     launch_ln<kH>(at<float>(ws, L.pre), nullptr, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo),
                   w.ln1_g, w.ln1_b, M, nullptr, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), st);
   }
@@ -913,7 +913,7 @@ int run_layer(syl_handle* h, int l, float* h_out, cudaStream_t st) {
     if ((rc = launch_gemm(h, pl.ffn2[l], st, h->sm_count))) return rc;
   }
   {
-    StageTimer tm(h, ST_LN, st);   // h = LN(h + ffn); fp32 only where the caller wants the layer output (h_out)
+    StageTimer tm(h, ST_LN_ENC, st);   // h = LN(h + ffn); fp32 only where the caller wants the layer output (h_out)
     launch_ln<kH>(at<float>(ws, L.pre), nullptr, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo),
                   w.ln2_g, w.ln2_b, M, h_out, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), st);
   }
@@ -925,8 +925,8 @@ int run_segment(const float* states, int B, int T, float thr_norm, float thr_mer
                 float* seg_feat, int max_seg, float* nsq, int32_t* scratch, cudaStream_t st) {
   const int rows = B * T;
   float* pw = nsq + rows;      // powf(nsq, .5f) per frame, right behind the squared norms
-  launch_pdl(frame_sqnorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, states, rows, nsq, pw);
-  launch_pdl(segment_kernel, dim3(B), dim3(32), 0, st, states, nsq, pw, T, thr_norm, thr_merge, seg, seg_count, max_seg, scratch);
+  launch_pdl(frame_sqnorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, states, rows, thr_norm, nsq, pw);
+  launch_pdl(segment_kernel, dim3(B), dim3(SEG_SCAN_THREADS), 0, st, states, pw, T, thr_merge, seg, seg_count, max_seg, scratch);
   if (seg_feat) launch_pdl(segment_pool_kernel, dim3(max_seg, B), dim3(192), 0, st, states, T, seg, seg_count, max_seg, seg_feat);
   return launch_ok() ? SYL_OK : SYL_E_CUDA;
 }

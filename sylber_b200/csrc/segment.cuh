@@ -148,10 +148,11 @@ __device__ __forceinline__ float np_sum_serial(const float* a, int n) { return _
 
 // ----------------------------------------------------------------------------------------------
 // per-frame squared norms + eps, one warp per frame:  nsq[i] = (x_i**2).sum() + 1e-8   (float32), and
-// pw[i] = powf(nsq[i], .5f) - the denominator the scalar cossim of the scan uses for frame i (segment_utils.py:96)
+// pw[i] = +-powf(nsq[i], .5f) - the denominator the scalar cossim of the scan uses for frame i (segment_utils.py:96),
+// with the sign carrying the norm-threshold decision of segment_utils.py:76 (array path: sqrt): negative = masked off
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-frame_sqnorm_kernel(const float* __restrict__ states, int rows, float* __restrict__ nsq, float* __restrict__ pw) {
+frame_sqnorm_kernel(const float* __restrict__ states, int rows, float thr_norm, float* __restrict__ nsq, float* __restrict__ pw) {
   griddep_launch_dependents();
   griddep_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -163,7 +164,8 @@ frame_sqnorm_kernel(const float* __restrict__ states, int rows, float* __restric
   if (lane == 0) {
     const float v = __fadd_rn(s, 1e-8f);
     nsq[row] = v;
-    pw[row] = powf_half(v);
+    const float p = powf_half(v);        // > 0 for every finite v >= 1e-8; NaN stays NaN and compares "off" like NumPy's >=
+    pw[row] = (__fsqrt_rn(v) >= thr_norm) ? p : -p;
   }
 }
 
@@ -203,17 +205,20 @@ __device__ __forceinline__ void lane_mean_rows(LaneVec& acc, const float* __rest
 //   seg     [B, max_seg, 2] int32 out  seg_count [B] out
 //   scratch [B, 6*(T+1)] int32/float workspace (segment starts/ends/dead flags, boundaries, sweep sims)
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32)
-segment_kernel(const float* __restrict__ states_all, const float* __restrict__ nsq_all, const float* __restrict__ pw_all, int T,
-               float thr_norm, float thr_merge, int32_t* __restrict__ seg_all, int32_t* __restrict__ seg_count, int max_seg,
-               int32_t* __restrict__ scratch_all) {
+constexpr int SEG_SCAN_THREADS = 96;     // warps 0, 1: the scan; warp 2: one thread that keeps the row ring full
+
+__global__ void __launch_bounds__(SEG_SCAN_THREADS)
+segment_kernel(const float* __restrict__ states_all, const float* __restrict__ pw_all, int T, float thr_merge,
+               int32_t* __restrict__ seg_all, int32_t* __restrict__ seg_count, int max_seg, int32_t* __restrict__ scratch_all) {
   __shared__ __align__(128) float ring[SEG_RING][SEG_ROW_FLOATS];
   __shared__ __align__(8) uint64_t full_bar[SEG_RING];
+  __shared__ __align__(8) uint64_t empty_bar[SEG_RING];
+  __shared__ float2 part[2][2];          // [frame parity][warp]: partial sums of (curr*x) and (cand*cand)
   griddep_launch_dependents();
   const int b = blockIdx.x;
   const int lane = lane_id();
+  const int w = threadIdx.x >> 5;
   const float* states = states_all + (size_t)b * T * SEG_D;
-  const float* nsq = nsq_all + (size_t)b * T;
   const float* pw = pw_all + (size_t)b * T;
   int32_t* scratch = scratch_all + (size_t)b * 6 * (T + 1);
   int32_t* seg_s = scratch;
@@ -222,101 +227,132 @@ segment_kernel(const float* __restrict__ states_all, const float* __restrict__ n
   int32_t* mid_seg = scratch + 3 * (T + 1);
   float* sim_prev = reinterpret_cast<float*>(scratch + 4 * (T + 1));
   float* sim_next = reinterpret_cast<float*>(scratch + 5 * (T + 1));
-  if (lane == 0) {
+  if (threadIdx.x == 0) {
 #pragma unroll
-    for (int k = 0; k < SEG_RING; ++k) mbar_init(&full_bar[k], 1);
+    for (int k = 0; k < SEG_RING; ++k) {
+      mbar_init(&full_bar[k], 1);
+      mbar_init(&empty_bar[k], 2);       // one arrival per scan warp
+    }
     fence_barrier_init();
   }
-  __syncwarp();
+  __syncthreads();
   griddep_wait();
 
-  // row `r` of the utterance -> ring slot r % SEG_RING: lane 0 arms the barrier, lanes 0..7 copy one 384-byte block each
-  auto prefetch = [&](int r) {
-    if (r >= T) return;
-    const int slot = r % SEG_RING;
-    if (lane == 0) mbar_arrive_expect_tx(&full_bar[slot], SEG_D * sizeof(float));
-    __syncwarp();
-    if (lane < 8) bulk_copy_g2s(&ring[slot][SEG_BLK_PAD * lane], states + (size_t)r * SEG_D + 96 * lane, 96 * sizeof(float), &full_bar[slot]);
-  };
-  for (int r = 0; r < SEG_RING; ++r) prefetch(r);
+  if (w == 2) {
+    // ---- producer: row r of the utterance -> ring slot r % SEG_RING as eight 384-byte bulk copies (one per pairwise
+    // block, into the padded image), re-armed as soon as both scan warps have released the slot
+    if (lane == 0) {
+      for (int r = 0; r < T; ++r) {
+        const int slot = r % SEG_RING;
+        if (r >= SEG_RING) mbar_wait(&empty_bar[slot], (uint32_t)(r / SEG_RING - 1) & 1u);
+        mbar_arrive_expect_tx(&full_bar[slot], SEG_D * sizeof(float));
+        const float* src = states + (size_t)r * SEG_D;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bulk_copy_g2s(&ring[slot][SEG_BLK_PAD * k], src + 96 * k, 96 * sizeof(float), &full_bar[slot]);
+      }
+    }
+    return;
+  }
 
   int nseg = 0, nmid = 0;
-  // ---- phase 1: greedy scan (segment_utils.py:79-108) ----
+  // ---- phase 1: greedy scan (segment_utils.py:79-108), TWO warps per utterance ----
+  // Lane (g, a) of warp w owns accumulator a of pairwise block 4 w + g, i.e. the 12 elements 96 (4 w + g) + 8 m + a: the
+  // in-lane chain is NumPy's sequential accumulation, xor-shuffles 1, 2, 4 are its tree inside a block, 8 and 16 the
+  // tree over the warp's four blocks, and the two warps exchange one float2 through shared memory for the last level.
+  // Both warps evaluate every decision redundantly (identical inputs, identical operations), so control flow stays
+  // uniform.  The step is latency bound (one warp per scheduler, dependent chains), hence: selects instead of branches,
+  // and powf of the merged centroid's norm deferred to the next scoring frame, where it overlaps that frame's dot product.
   {
-    float curr[SEG_PER_LANE];
-    float p_curr = 0.0f;   // powf((curr**2).sum() + 1e-8, .5f)
+    constexpr int E = 12;
+    const int ring_off = SEG_BLK_PAD * (4 * w + (lane >> 3)) + (lane & 7);
+    float curr[E];
+#pragma unroll
+    for (int m = 0; m < E; ++m) curr[m] = 0.0f;
+    float p_curr = 1.0f;        // powf((curr**2).sum() + 1e-8, .5f), valid unless pow_pending
+    float sq_pending = 1.0f;    // (curr**2).sum() + 1e-8 of a centroid merged in the previous scoring frame
+    bool pow_pending = false;
     int cnt = 0, s = -1;
     for (int i0 = 0; i0 < T; i0 += 32) {
-      const int idx = min(i0 + lane, T - 1);
-      const float my_sq = nsq[idx], my_pw = pw[idx];
+      const float my_pw = pw[min(i0 + lane, T - 1)];
       const int n_here = min(32, T - i0);
       for (int j = 0; j < n_here; ++j) {
         const int i = i0 + j;
-        const float xsq = __shfl_sync(0xffffffffu, my_sq, j), px = __shfl_sync(0xffffffffu, my_pw, j);
+        const float pxs = __shfl_sync(0xffffffffu, my_pw, j);
+        const bool on = pxs > 0.0f;
+        const float px = fabsf(pxs);
         const int slot = i % SEG_RING;
         mbar_wait(&full_bar[slot], (uint32_t)(i / SEG_RING) & 1u);
-        const bool on = __fsqrt_rn(xsq) >= thr_norm;    // array path: `** .5` on an ndarray is sqrt
+        float x[E];
+        if (on) {
+          const float* row = &ring[slot][ring_off];
+#pragma unroll
+          for (int m = 0; m < E; ++m) x[m] = row[8 * m];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[slot]);    // every lane's loads of the slot are issued: the producer may refill it
         if (!on) {
-          prefetch(i + SEG_RING);                        // the slot was never read: nothing to order
           if (s > -1) {
-            if (lane == 0) { seg_s[nseg] = s; seg_e[nseg] = i; }
+            if (threadIdx.x == 0) { seg_s[nseg] = s; seg_e[nseg] = i; }
             ++nseg;
           }
           s = -1;
           cnt = 0;
           continue;
         }
-        float x[SEG_PER_LANE];
-        lane_load_smem(x, ring[slot], lane);
-        // every lane holds its part of the row in registers before the async proxy may overwrite the slot
-        asm volatile("" ::"f"(x[0]), "f"(x[23]) : "memory");
-        __syncwarp();
-        prefetch(i + SEG_RING);
-        if (cnt == 0) {
+        if (cnt == 0) {                                  // first frame of a run
 #pragma unroll
-          for (int k = 0; k < SEG_PER_LANE; ++k) curr[k] = x[k];
+          for (int m = 0; m < E; ++m) curr[m] = x[m];
           p_curr = px;
+          pow_pending = false;
           cnt = 1;
           s = i;
           continue;
         }
-        // the decision ...
-        float a0 = __fmul_rn(curr[0], x[0]), a1 = __fmul_rn(curr[1], x[1]);
+        // denominator of the current centroid (independent of everything below until the division)
+        const float p_deferred = powf_half(sq_pending);
+        p_curr = pow_pending ? p_deferred : p_curr;
+        // the decision's dot product ...
+        float a0 = __fmul_rn(curr[0], x[0]);
 #pragma unroll
-        for (int m = 1; m < 12; ++m) {
-          a0 = __fadd_rn(a0, __fmul_rn(curr[2 * m], x[2 * m]));
-          a1 = __fadd_rn(a1, __fmul_rn(curr[2 * m + 1], x[2 * m + 1]));
-        }
+        for (int m = 1; m < E; ++m) a0 = __fadd_rn(a0, __fmul_rn(curr[m], x[m]));
         // ... and, speculatively, the merged centroid with its squared norm (independent of the decision)
         const float fc = (float)cnt, fc1 = (float)(cnt + 1), rc1 = __frcp_rn(fc1);
-        float cand[SEG_PER_LANE];
+        float num[E], cand[E];
+        bool tiny = false;
 #pragma unroll
-        for (int k = 0; k < SEG_PER_LANE; ++k) cand[k] = div_by_count(__fadd_rn(__fmul_rn(curr[k], fc), x[k]), fc1, rc1);
-        float b0 = __fmul_rn(cand[0], cand[0]), b1 = __fmul_rn(cand[1], cand[1]);
-#pragma unroll
-        for (int m = 1; m < 12; ++m) {
-          b0 = __fadd_rn(b0, __fmul_rn(cand[2 * m], cand[2 * m]));
-          b1 = __fadd_rn(b1, __fmul_rn(cand[2 * m + 1], cand[2 * m + 1]));
+        for (int m = 0; m < E; ++m) {
+          num[m] = __fadd_rn(__fmul_rn(curr[m], fc), x[m]);
+          const float q0 = __fmul_rn(num[m], rc1);
+          cand[m] = __fmaf_rn(__fmaf_rn(-q0, fc1, num[m]), rc1, q0);     // div_by_count without its guard ...
+          tiny |= !(fabsf(num[m]) > 1e-30f);
         }
-        float sxy = __fadd_rn(a0, a1), sqq = __fadd_rn(b0, b1);
+        if (__any_sync(0xffffffffu, tiny)) {                              // ... which is taken once for all elements
+#pragma unroll
+          for (int m = 0; m < E; ++m) cand[m] = __fdiv_rn(num[m], fc1);
+        }
+        float b0 = __fmul_rn(cand[0], cand[0]);
+#pragma unroll
+        for (int m = 1; m < E; ++m) b0 = __fadd_rn(b0, __fmul_rn(cand[m], cand[m]));
 #pragma unroll
         for (int o = 1; o <= 16; o <<= 1) {
-          sxy = __fadd_rn(sxy, __shfl_xor_sync(0xffffffffu, sxy, o));
-          sqq = __fadd_rn(sqq, __shfl_xor_sync(0xffffffffu, sqq, o));
+          a0 = __fadd_rn(a0, __shfl_xor_sync(0xffffffffu, a0, o));
+          b0 = __fadd_rn(b0, __shfl_xor_sync(0xffffffffu, b0, o));
         }
-        const float xy = __fadd_rn(0.0f, sxy);
-        const float p_cand = powf_half(__fadd_rn(__fadd_rn(0.0f, sqq), 1e-8f));
+        if (lane == 0) part[i & 1][w] = make_float2(a0, b0);
+        named_bar_sync(1, 64);                           // the two scan warps' partials are visible to each other
+        const float2 other = part[i & 1][w ^ 1];
+        const float xy = __fadd_rn(0.0f, __fadd_rn(a0, other.x));
+        const float sq_cand = __fadd_rn(__fadd_rn(0.0f, __fadd_rn(b0, other.y)), 1e-8f);
         const float sim = __fdiv_rn(__fdiv_rn(xy, p_curr), px);   // scalar path: powf denominators
-        cnt += 1;             // also after a split: reference quirk (segment_utils.py:103)
-        if (sim >= thr_merge) {
+        const bool merge = sim >= thr_merge;
+        cnt += 1;               // also after a split: reference quirk (segment_utils.py:103)
 #pragma unroll
-          for (int k = 0; k < SEG_PER_LANE; ++k) curr[k] = cand[k];
-          p_curr = p_cand;
-        } else {
-#pragma unroll
-          for (int k = 0; k < SEG_PER_LANE; ++k) curr[k] = x[k];
-          p_curr = px;
-          if (lane == 0) { seg_s[nseg] = s; seg_e[nseg] = i; mid_bd[nmid] = i; mid_seg[nmid] = nseg; }
+        for (int m = 0; m < E; ++m) curr[m] = merge ? cand[m] : x[m];
+        pow_pending = merge;
+        sq_pending = sq_cand;
+        p_curr = merge ? p_curr : px;
+        if (!merge) {
+          if (threadIdx.x == 0) { seg_s[nseg] = s; seg_e[nseg] = i; mid_bd[nmid] = i; mid_seg[nmid] = nseg; }
           ++nseg;
           ++nmid;
           s = i;
@@ -324,10 +360,11 @@ segment_kernel(const float* __restrict__ states_all, const float* __restrict__ n
       }
     }
     if (s > -1) {
-      if (lane == 0) { seg_s[nseg] = s; seg_e[nseg] = T; }
+      if (threadIdx.x == 0) { seg_s[nseg] = s; seg_e[nseg] = T; }
       ++nseg;
     }
   }
+  if (w != 0) return;      // phases 2 and 3 run on warp 0 (its lane 0 wrote the segment arrays)
   __syncwarp();
 
   // ---- phase 2: boundary merge / refinement, in order (segment_utils.py:110-128) ----

@@ -46,8 +46,8 @@ def test_pure_host_entry_points(lib):
     assert 0 < b1 < b32 < 8 * 2 ** 30
     assert b32 % 1024 == 0
     assert lib.syl_segment_workspace_bytes(4, 499) > 4 * 499 * 4
-    assert lib.syl_num_stages() == 12
-    assert lib.syl_stage_name(1) == b"conv2_6_gemm" and lib.syl_stage_name(11) == b"conv1_gemm"
+    assert lib.syl_num_stages() == 13
+    assert lib.syl_stage_name(1) == b"conv2_6_gemm" and lib.syl_stage_name(11) == b"conv1_gemm" and lib.syl_stage_name(12) == b"layernorm_encoder"
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
