@@ -324,6 +324,17 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the GPU arm has no CPU fallback (use --impl reference for the CPU path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = None
+    if world > 1 and hasattr(os, "sched_setaffinity"):
+        # one process per GPU on one host: give every rank its own share of the host cores, so that the ranks' launch /
+        # packaging threads do not migrate over each other (measured: e2e at 4 ranks, profiles/r03_multi_gpu.md)
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // world
+        if per >= 1:
+            mine_cores = cores[local * per:(local + 1) * per]
+            os.sched_setaffinity(0, mine_cores)
+            torch.set_num_threads(max(1, min(per, 4)))
+            affinity = f"{per} of {len(cores)} host cores per rank"
     if world > 1:
         # NCCL prints its version banner on stdout when NCCL_DEBUG is set; keep stdout for the one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -533,7 +544,7 @@ def run_ours(args):
         "config": {"workload": f"{desc}, sylber_base ({layers}L/768d), 1xB200 per rank", "weights": wsrc,
                    "frames_padded_per_clip": T, "clips_per_gpu": B, "valid_frames_per_step": int(frames_valid),
                    "padded_frames_per_step": int(world * B * T), "t_max_definition": "global maximum over all ranks' clips",
-                   "mode": args.mode, "parallelism": f"dp{world} by utterance",
+                   "mode": args.mode, "parallelism": f"dp{world} by utterance", "host_affinity": affinity,
                    "l2": "per-step working set (~4 GB of activations) exceeds the 126 MB L2; no explicit flush",
                    "segments_per_clip_mean": float(seg_counts.mean()),
                    "e2e_input": f"list of {B} (1, n) fp32 views of pinned host memory"

@@ -151,6 +151,12 @@ int syl_powf_half(const float* x, float* y, int64_t n, void* stream);
 /* copy an intermediate of the most recent syl_forward / syl_conv_frontend out as fp32.
  * names: conv0..conv6 ([batch, L_i, 512]), proj, pos, enc_in ([batch, T, 768]) */
 int syl_read_stage(syl_handle* h, const char* name, float* out, size_t n_floats, void* stream);
+/* fp16 range check (diagnostic, off the hot path): scans the fp16 activation buffers the most recent forward on this
+ * handle left in its workspace (conv0-5 outputs, LayerNorm(512) output, residual stream, QKV, attention context, FFN
+ * intermediate - the last layer's for the per-layer ones) and writes to *count_dev (one uint64 on the device) how many
+ * elements sit at the saturation value +-65504 or are not finite.  Every fp16 store of the forward saturates instead
+ * of overflowing, so a non-zero count means this input + checkpoint leaves the fp16 range somewhere. */
+int syl_saturation_scan(syl_handle* h, unsigned long long* count_dev, void* stream);
 /* run only the first n encoder layers in syl_forward (debug / per-layer parity); n < 0 restores all */
 int syl_set_active_layers(syl_handle* h, int n);
 /* how many kernels of this library syl_forward launches for the given shape (bench.py reports it) */

@@ -51,6 +51,7 @@ SIGNATURES = {
                               _c_int, _c_void_p, _c_size_t, _c_void_p]),
     "syl_powf_half": (_c_int, [_c_void_p, _c_void_p, ctypes.c_int64, _c_void_p]),
     "syl_read_stage": (_c_int, [_c_void_p, ctypes.c_char_p, _c_void_p, _c_size_t, _c_void_p]),
+    "syl_saturation_scan": (_c_int, [_c_void_p, _c_void_p, _c_void_p]),
     "syl_set_active_layers": (_c_int, [_c_void_p, _c_int]),
     "syl_forward_launch_count": (_c_int, [_c_void_p, _c_int]),
     "syl_set_graph_mode": (_c_int, [_c_void_p, _c_int]),

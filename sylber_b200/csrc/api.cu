@@ -194,6 +194,18 @@ __global__ void fill_i32_kernel(int32_t* p, int n, int v) {
   if (i < n) p[i] = v;
 }
 
+// fp16 range check (diagnostic, off the hot path): counts elements that sit at the saturation value +-65504 or are not
+// finite.  Every fp16 store of the forward saturates instead of overflowing (pack_f16x2_sat, split_pair), so a non-zero
+// count means an activation left the fp16 range and the result of that forward is not trustworthy in this precision.
+__global__ void count_saturated_kernel(const __half* __restrict__ x, size_t n, unsigned long long* __restrict__ count) {
+  unsigned long long local = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned short b = __half_as_ushort(x[i]) & 0x7fffu;
+    local += (b >= 0x7bffu) ? 1u : 0u;
+  }
+  if (local) atomicAdd(count, local);
+}
+
 __global__ void powf_half_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = powf_half(x[i]);
@@ -1475,6 +1487,29 @@ int syl_powf_half(const float* x, float* y, int64_t n, void* stream) {
   if (!x || !y || n <= 0) return SYL_E_ARG;
   powf_half_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, n);
   return launch_ok() ? SYL_OK : SYL_E_CUDA;
+}
+
+int syl_saturation_scan(syl_handle* h, unsigned long long* count_dev, void* stream) {
+  SYL_ENTER();
+  if (!h || !count_dev) return SYL_E_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard dg(h->device);
+  if (!h->plans[h->plan_cur].valid) return fail(h, SYL_E_STATE, "syl_saturation_scan: no forward has run yet");
+  const Plan& pl = h->plans[h->plan_cur];
+  const WsLayout& L = pl.lay;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t B = pl.batch, M = B * L.T;
+  CUDA_TRY(h, cudaMemsetAsync(count_dev, 0, sizeof(unsigned long long), st));
+  auto scan = [&](size_t off, size_t n) {
+    count_saturated_kernel<<<grid_for(n), 256, 0, st>>>(at<__half>(pl.ws, off), n, count_dev);
+  };
+  for (int i = 0; i < 6; ++i) scan(L.act_hi[i], B * L.L[i] * kC);     // conv0 .. conv5 activations
+  scan(L.ln_hi, M * kC);
+  scan(L.h16_hi, M * kH);                                            // residual stream (last layer's state)
+  scan(L.qkv, M * 3 * kH);
+  scan(L.ctx_hi, M * kH);
+  scan(L.mid_hi, M * kF);
+  return launch_ok() ? SYL_OK : fail(h, SYL_E_CUDA, "syl_saturation_scan launch failed: %s", launch_err());
 }
 
 int syl_num_stages(void) { return ST_COUNT; }

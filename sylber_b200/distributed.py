@@ -115,34 +115,51 @@ def segment_sharded(segmenter, wav_file=None, wav=None, in_second=True, group=No
         else:
             local_max = max((int(torch.as_tensor(w).shape[-1]) for w in local_kw["wav"]), default=0)
             pad_to = global_max_length(local_max, device=dev, group=group)
-    local = segmenter(in_second=False, pad_to=pad_to, **local_kw) if mine else []
-    # (1) counts, (2) fixed-stride table
     per_rank = max(sizes)
-    cnt = torch.zeros(per_rank, dtype=torch.int32)
-    for k, r in enumerate(local):
-        cnt[k] = len(r["segments"])
-    all_cnt = torch.empty(world * per_rank, dtype=torch.int32, device=dev)
-    dist.all_gather_into_tensor(all_cnt, cnt.to(dev), group=group)
-    all_cnt_h = all_cnt.cpu()
-    stride = max(int(all_cnt_h.max()), 1)
-    seg = torch.zeros((per_rank, stride, 2), dtype=torch.int32)
-    for k, r in enumerate(local):
-        n = int(cnt[k])
-        if n:
-            seg[k, :n] = torch.from_numpy(np.asarray(r["segments"], dtype=np.int32).reshape(-1, 2))
-    all_seg = torch.empty((world * per_rank, stride, 2), dtype=torch.int32, device=dev)
-    dist.all_gather_into_tensor(all_seg, seg.to(dev), group=group)
-    all_seg_h = all_seg.cpu().numpy()
     all_feat_h = None
-    if gather_features:
-        feat = torch.zeros((per_rank, stride, 768), dtype=torch.float32)
+    if hasattr(segmenter, "call_with_tables") and not gather_features:
+        # fast path: the device-side segment table goes into the collective as it is - ONE all-gather of a
+        # (per_rank, 1 + T, 2) int32 block whose row 0 carries the count, then one device->host copy
+        T = segmenter._engine.num_frames(pad_to)
+        block = torch.zeros((per_rank, 1 + T, 2), dtype=torch.int32, device=segmenter._engine.device)
+        if mine:
+            local, seg_dev, cnt_dev = segmenter.call_with_tables(local_kw["wav"], pad_to=pad_to)
+            block[:len(mine), 1:] = seg_dev
+            block[:len(mine), 0, 0] = cnt_dev
+        else:
+            local = []
+        block = block.to(dev)
+        gathered = torch.empty((world * per_rank, 1 + T, 2), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(gathered, block, group=group)
+        g = gathered.cpu().numpy()
+        all_cnt_h, all_seg_h = g[:, 0, 0], g[:, 1:]
+    else:
+        local = segmenter(in_second=False, pad_to=pad_to, **local_kw) if mine else []
+        # (1) counts, (2) fixed-stride table
+        cnt = torch.zeros(per_rank, dtype=torch.int32)
+        for k, r in enumerate(local):
+            cnt[k] = len(r["segments"])
+        all_cnt = torch.empty(world * per_rank, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(all_cnt, cnt.to(dev), group=group)
+        all_cnt_h = all_cnt.cpu().numpy()
+        stride = max(int(all_cnt_h.max()), 1)
+        seg = torch.zeros((per_rank, stride, 2), dtype=torch.int32)
         for k, r in enumerate(local):
             n = int(cnt[k])
             if n:
-                feat[k, :n] = torch.from_numpy(np.ascontiguousarray(r["segment_features"]))
-        all_feat = torch.empty((world * per_rank, stride, 768), dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(all_feat, feat.to(dev), group=group)
-        all_feat_h = all_feat.cpu().numpy()
+                seg[k, :n] = torch.from_numpy(np.asarray(r["segments"], dtype=np.int32).reshape(-1, 2))
+        all_seg = torch.empty((world * per_rank, stride, 2), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(all_seg, seg.to(dev), group=group)
+        all_seg_h = all_seg.cpu().numpy()
+        if gather_features:
+            feat = torch.zeros((per_rank, stride, 768), dtype=torch.float32)
+            for k, r in enumerate(local):
+                n = int(cnt[k])
+                if n:
+                    feat[k, :n] = torch.from_numpy(np.ascontiguousarray(r["segment_features"]))
+            all_feat = torch.empty((world * per_rank, stride, 768), dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(all_feat, feat.to(dev), group=group)
+            all_feat_h = all_feat.cpu().numpy()
     out = []
     for r in range(world):
         for k in range(sizes[r]):

@@ -304,6 +304,14 @@ class _Engine:
         _lib.check(self.lib, self.handle, rc, f"syl_read_stage({name})")
         return out
 
+    def saturation_count(self):
+        """How many fp16 activations of the most recent forward sit at +-65504 / are not finite (syl_saturation_scan)."""
+        out = torch.zeros(1, dtype=torch.int64, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self.lib.syl_saturation_scan(self.handle, _ptr(out), ctypes.c_void_p(stream))
+        _lib.check(self.lib, self.handle, rc, "syl_saturation_scan")
+        return int(out.item())
+
     def set_active_layers(self, n):
         _lib.check(self.lib, self.handle, self.lib.syl_set_active_layers(self.handle, int(n)), "syl_set_active_layers")
 
@@ -465,10 +473,12 @@ class Segmenter:
         """(lo, hi) sub-batch bounds of one padded batch of n_rows rows (batching.sub_batch_bounds)."""
         return sub_batch_bounds(n_rows, self.streams, self.max_batch, self.sub_batch_sizes)
 
-    def _run_jobs(self, rows, lengths, jobs, pcm=0):
+    def _run_jobs(self, rows, lengths, jobs, pcm=0, tables=None):
         """Padded batches through the engine.  rows: 1-D fp32 CPU tensors (or int16 at `pcm` Hz when pcm != 0); jobs: list of
         (row indices, max_length) - every row of a job is padded to that job's max_length (results depend on it, 8a).
         Returns per row (segments int64 (N,2) | empty, segment_features (N,768) | empty, hidden).
+        `tables` = (seg (R, T, 2) int32, cnt (R,) int32) device tensors: every sub-batch also leaves its fixed-stride
+        segment table there, at its rows (single-job calls only) - what segment_sharded all-gathers.
 
         All sub-batches of all jobs are launched first, round-robin over the streams (a sub-batch's host->device /
         device->host copies overlap the others' kernels), and collected afterwards."""
@@ -517,6 +527,9 @@ class Segmenter:
                 else:
                     wav_dev, n_dev = eng.upload(chunk, sub_len, max_length, slot)
                 hidden, seg, cnt, feat = eng.forward(wav_dev, n_dev, thr_n, thr_m, slot=slot)
+                if tables is not None:
+                    tables[0][idx[0]:idx[-1] + 1].copy_(seg, non_blocking=True)
+                    tables[1][idx[0]:idx[-1] + 1].copy_(cnt, non_blocking=True)
                 cnt_pin = torch.empty(cnt.shape, dtype=torch.int32, pin_memory=True)
                 cnt_pin.copy_(cnt, non_blocking=True)
                 seg_pin = torch.empty(seg.shape, dtype=torch.int32, pin_memory=True)     # fixed-stride table: B x T x 2 int32
@@ -581,6 +594,34 @@ class Segmenter:
         outputs = [{'segments': seg * 1.0 / FRAME_RATE if in_second else seg,
                     'segment_features': feat, 'hidden_states': hid} for seg, feat, hid in results]
         return outputs if is_batch else outputs[0]
+
+    def fp16_saturated(self):
+        """Diagnostic for a new checkpoint / input domain: number of fp16 activations of the most recent forward that hit
+        the saturation value (0 = every intermediate stayed inside the fp16 range, which the precision claims assume).
+        Scans the workspace of the forward that ran last; not on the hot path."""
+        torch.cuda.synchronize(self._engine.device)
+        return self._engine.saturation_count()
+
+    @torch.no_grad()
+    def call_with_tables(self, wav, pad_to=None):
+        """`__call__(wav=list, in_second=False, pad_to=...)` that also returns the call's fixed-stride segment table as
+        DEVICE tensors, seg (B, T, 2) int32 and cnt (B,) int32 with T = frames of the padded length: the operands of the
+        one collective of the sharded path (distributed.segment_sharded), gathered without a host round trip."""
+        if self.bucket_ratio:
+            raise ValueError("call_with_tables pads the whole call to one length; it cannot be combined with bucket_ratio")
+        rows = []
+        for w in wav:
+            w = torch.as_tensor(w)
+            rows.extend(w[i] for i in range(w.shape[0])) if w.dim() == 2 else rows.append(w)
+        lengths = [int(r.shape[-1]) for r in rows]
+        max_length = max(max(lengths), int(pad_to or 0))
+        eng = self._engine
+        T = eng.num_frames(max_length)
+        seg = torch.empty((len(rows), T, 2), dtype=torch.int32, device=eng.device)
+        cnt = torch.empty((len(rows),), dtype=torch.int32, device=eng.device)
+        results = self._run_jobs(rows, lengths, [(list(range(len(rows))), max_length)], tables=(seg, cnt))
+        outputs = [{'segments': sg, 'segment_features': feat, 'hidden_states': hid} for sg, feat, hid in results]
+        return outputs, seg, cnt
 
     @torch.no_grad()
     def segment(self, input_values=None, features=None, attention_mask=None, mergethreshold=None, normthreshold=None,
