@@ -346,7 +346,7 @@ def run_ours(args):
     B = len(clips)
     max_batch = 32
     seg = Segmenter(model_ckpt=None, state_dict=sd, encoding_layer=layers, device=f"cuda:{local}", mode=args.mode,
-                    max_batch=max_batch, **({"streams": args.streams} if args.streams else {}))
+                    max_batch=max_batch, trim_padding=args.trim, **({"streams": args.streams} if args.streams else {}))
     eng = seg._engine
     lens = [c.shape[1] for c in clips]
     flops, T, L = stage_flops(pad_to, layers)           # executed work: every clip is padded to pad_to
@@ -544,7 +544,7 @@ def run_ours(args):
         "config": {"workload": f"{desc}, sylber_base ({layers}L/768d), 1xB200 per rank", "weights": wsrc,
                    "frames_padded_per_clip": T, "clips_per_gpu": B, "valid_frames_per_step": int(frames_valid),
                    "padded_frames_per_step": int(world * B * T), "t_max_definition": "global maximum over all ranks' clips",
-                   "mode": args.mode, "parallelism": f"dp{world} by utterance", "host_affinity": affinity,
+                   "mode": args.mode, "trim_padding": bool(args.trim), "parallelism": f"dp{world} by utterance", "host_affinity": affinity,
                    "l2": "per-step working set (~4 GB of activations) exceeds the 126 MB L2; no explicit flush",
                    "segments_per_clip_mean": float(seg_counts.mean()),
                    "e2e_input": f"list of {B} (1, n) fp32 views of pinned host memory"
@@ -604,6 +604,7 @@ def main():
     ap.add_argument("--mode", default="parity", choices=["parity", "strict", "fast", "exact"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / segment_agreement leg")
     ap.add_argument("--library-baseline", action="store_true", help="also time transformers.HubertModel eager on the GPU")
+    ap.add_argument("--trim", action="store_true", help="trimmed mode: padded frames are not computed (opt-in deviation)")
     ap.add_argument("--streams", type=int, default=0, help="sub-batches in flight in the e2e leg (0 = Segmenter default)")
     ap.add_argument("--workload", default="10s", choices=["10s", "60s", "mixed"],
                     help="10s = BASELINE configs[1]/[2] (batch 32 x 10 s per GPU, the metric's configuration); "

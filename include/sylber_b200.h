@@ -66,6 +66,14 @@ typedef struct syl_handle syl_handle;
 #define SYL_MODE_FAST 0                                                      /* single-pass fp16 everywhere */
 #define SYL_MODE_EXACT (SYL_SPLIT_CONV | SYL_SPLIT_CONV1 | SYL_SPLIT_PROJ | SYL_SPLIT_ENC)   /* 2.7e-5 */
 
+/* Option bit of the mode argument (not a precision site).  TRIMMED MODE, an opt-in deviation from the reference's
+ * padding semantics (sylber/model/sylber.py:93-126): the reference computes, returns and segments the padded frames of
+ * a short utterance in a batch; with this bit the frames beyond an utterance's valid length are NOT computed - conv,
+ * GEMM and attention tiles that lie entirely in the padding are skipped, hidden rows >= valid_frames[b] come back as
+ * zeros and therefore carry no segments.  Valid frames are unchanged: they still see the batch-wide padded length
+ * through the conv-0 GroupNorm statistics, exactly as in the reference (tests/test_gpu_trim.py). */
+#define SYL_TRIM_PADDING 4096
+
 #define SYL_DTYPE_F32 0
 
 /* ---- lifecycle: replaces HubertModel(config) + load_state_dict (sylber/model/sylber.py:41,51-54) ---- */

@@ -13,6 +13,7 @@ _SO = os.path.join(_PKG, "libsylber_b200.so")
 SYL_SPLIT_CONV, SYL_SPLIT_PROJ, SYL_SPLIT_ENC, SYL_SPLIT_CONV1 = 1, 2, 4, 8
 SYL_SPLIT_CONV2, SYL_SPLIT_CONV3, SYL_SPLIT_CONV4, SYL_SPLIT_CONV5, SYL_SPLIT_CONV6 = 16, 32, 64, 128, 256
 SYL_SPLIT_FPROJ, SYL_SPLIT_POS = 512, 1024
+SYL_TRIM_PADDING = 4096
 MODES = {
     "parity": SYL_SPLIT_CONV4 | SYL_SPLIT_CONV5 | SYL_SPLIT_CONV6 | SYL_SPLIT_FPROJ,
     "strict": SYL_SPLIT_CONV | SYL_SPLIT_CONV1 | SYL_SPLIT_PROJ,

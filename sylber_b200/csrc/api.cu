@@ -180,13 +180,25 @@ __global__ void add_inplace_kernel(float* __restrict__ x, const float* __restric
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] += y[i];
 }
 
+// valid[b] = frames of utterance b that come from real samples (modeling_hubert.py:675-700), clamped to [1, T];
+// valid[(1 + i) * batch + b] = rows of conv layer i (0..6) those frames read - what the trimmed mode computes
+// (backwards through the receptive fields: rows_i = (rows_{i+1} - 1) * stride_{i+1} + kernel_{i+1})
 __global__ void valid_frames_kernel(const int32_t* __restrict__ n_samples, int batch, int T, int32_t* __restrict__ valid) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
-  int n = n_samples[b];
   const int k[7] = {10, 3, 3, 3, 3, 2, 2}, s[7] = {5, 2, 2, 2, 2, 2, 2};
-  for (int i = 0; i < 7; ++i) n = (n >= k[i]) ? (n - k[i]) / s[i] + 1 : 0;
-  valid[b] = max(1, min(n, T));
+  int n = n_samples ? n_samples[b] : 0x3fffffff;
+  if (n_samples) {
+    for (int i = 0; i < 7; ++i) n = (n >= k[i]) ? (n - k[i]) / s[i] + 1 : 0;
+  }
+  const int v = max(1, min(n, T));
+  valid[b] = v;
+  int need = v;
+  valid[7 * batch + b] = need;                       // conv6 output rows = frames
+  for (int i = 5; i >= 0; --i) {
+    need = (need - 1) * s[i + 1] + k[i + 1];
+    valid[(1 + i) * batch + b] = need;
+  }
 }
 
 __global__ void fill_i32_kernel(int32_t* p, int n, int v) {
@@ -336,6 +348,7 @@ struct syl_handle {
   int n_layers = 9;
   int active_layers = -1;
   int mode = SYL_MODE_PARITY;
+  bool trim = false;      // SYL_TRIM_PADDING: padded frames are not computed (opt-in deviation, include/sylber_b200.h)
   bool finalized = false;
   std::string err;
   std::map<std::string, std::pair<float*, std::vector<int64_t>>> raw;
@@ -518,7 +531,7 @@ WsLayout make_layout(int batch, int t_samp) {
   w.mom = take(B * (size_t)((w.L[0] + MOM_T_PER_BLOCK - 1) / MOM_T_PER_BLOCK) * C0_NMOM * sizeof(double));
   w.gn_scale = take(B * kC * sizeof(float));
   w.gn_shift = take(B * kC * sizeof(float));
-  w.valid = take(B * sizeof(int32_t));
+  w.valid = take(8 * B * sizeof(int32_t));   // frames, then needed rows of conv0..conv6 (valid_frames_kernel)
   w.nsq = take(2 * M * sizeof(float));   // squared norms, then their scalar powf (segment.cuh)
   w.seg_scratch = take(B * 6 * (size_t)(w.T + 1) * sizeof(int32_t));
   for (int i = 0; i < 6; ++i) {
@@ -708,6 +721,10 @@ int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
     op.p.N = kC;
     op.p.n_pass = conv_split(h->mode, i) ? 3 : 1;
     op.p.act = 1;
+    if (h->trim) {      // only the rows the valid frames read; the rest of a computed tile is written as zero
+      op.p.valid_rows = at<int32_t>(ws, L.valid) + (1 + i) * batch;
+      op.p.skip_invalid_tiles = 1;
+    }
     // the lo half of this layer's output is only needed if the NEXT conv runs split
     const bool ok = (i < 6) ? make_o_maps(h, op, nullptr, at<__half>(ws, L.act_hi[i]),
                                           conv_split(h->mode, i + 1) ? at<__half>(ws, L.act_lo[i]) : nullptr, kC)
@@ -746,6 +763,13 @@ int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
   }
   // encoder layers
   const int nl = h->n_layers;
+  // encoder GEMMs: one flat [B T, K] matrix, or (trimmed mode) tiled per utterance so that whole tiles of padding drop out
+  const int enc_rows = h->trim ? T : M, enc_batches = h->trim ? batch : 1;
+  auto enc_trim = [&](GemmOp& op) {
+    if (!h->trim) return;
+    op.p.valid_rows = at<int32_t>(ws, L.valid);
+    op.p.skip_invalid_tiles = 1;
+  };
   pl.qkv.assign(nl, GemmOp());
   pl.out.assign(nl, GemmOp());
   pl.ffn1.assign(nl, GemmOp());
@@ -756,7 +780,8 @@ int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
       GemmOp& op = pl.qkv[l];
       op.p = base_params();
       op.w = &w.qkv;
-      if (!make_a_maps(h, op, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), kH, M, 1, kH, (uint64_t)M * kH)) return SYL_E_CUDA;
+      if (!make_a_maps(h, op, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), kH, enc_rows, enc_batches, kH, (uint64_t)enc_rows * kH)) return SYL_E_CUDA;
+      enc_trim(op);
       op.p.N = 3 * kH;
       op.p.n_pass = split_enc ? 3 : 1;
       op.p.bias = w.qkv.bias;
@@ -768,7 +793,8 @@ int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
       GemmOp& op = pl.out[l];
       op.p = base_params();
       op.w = &w.out;
-      if (!make_a_maps(h, op, at<__half>(ws, L.ctx_hi), at<__half>(ws, L.ctx_lo), kH, M, 1, kH, (uint64_t)M * kH)) return SYL_E_CUDA;
+      if (!make_a_maps(h, op, at<__half>(ws, L.ctx_hi), at<__half>(ws, L.ctx_lo), kH, enc_rows, enc_batches, kH, (uint64_t)enc_rows * kH)) return SYL_E_CUDA;
+      enc_trim(op);
       op.p.N = kH;
       op.p.n_pass = split_enc ? 3 : 1;
       op.p.bias = w.out.bias;
@@ -778,7 +804,8 @@ int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
       GemmOp& op = pl.ffn1[l];
       op.p = base_params();
       op.w = &w.ffn1;
-      if (!make_a_maps(h, op, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), kH, M, 1, kH, (uint64_t)M * kH)) return SYL_E_CUDA;
+      if (!make_a_maps(h, op, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), kH, enc_rows, enc_batches, kH, (uint64_t)enc_rows * kH)) return SYL_E_CUDA;
+      enc_trim(op);
       op.p.N = kF;
       op.p.n_pass = split_enc ? 3 : 1;
       op.p.bias = w.ffn1.bias;
@@ -789,7 +816,8 @@ int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
       GemmOp& op = pl.ffn2[l];
       op.p = base_params();
       op.w = &w.ffn2;
-      if (!make_a_maps(h, op, at<__half>(ws, L.mid_hi), at<__half>(ws, L.mid_lo), kF, M, 1, kF, (uint64_t)M * kF)) return SYL_E_CUDA;
+      if (!make_a_maps(h, op, at<__half>(ws, L.mid_hi), at<__half>(ws, L.mid_lo), kF, enc_rows, enc_batches, kF, (uint64_t)enc_rows * kF)) return SYL_E_CUDA;
+      enc_trim(op);
       op.p.N = kH;
       op.p.n_pass = split_enc ? 3 : 1;
       op.p.bias = w.ffn2.bias;
@@ -811,17 +839,17 @@ int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
 
 template <int D>
 void launch_ln(const float* x, const float* add, const __half* add_hi, const __half* add_lo, const float* g, const float* b, int rows,
-               float* of, __half* ohi, __half* olo, cudaStream_t st) {
+               float* of, __half* ohi, __half* olo, cudaStream_t st, const int32_t* valid = nullptr, int T = 1) {
   constexpr int warps = 8;   // rows per block; 2 and 4 measured equal (profiles/r03_variants_ab.md)
   launch_pdl(layernorm_rows_kernel<D>, dim3((rows + warps - 1) / warps), dim3(warps * 32), 0, st, x, add, add_hi, add_lo, g, b, rows, of,
-             ohi, olo);
+             ohi, olo, valid, T);
 }
 
 long long* g_attn_trace = nullptr;   // set by syl_attention_trace for one launch
 int g_attn_trace_cap = 0;
 
 int launch_attention(const CUtensorMap& qkv, const CUtensorMap& o_hi, const CUtensorMap& o_lo, const int32_t* kv_len,
-                     int B, int T, int out_lo, int sm_count, cudaStream_t st) {
+                     int B, int T, int out_lo, int sm_count, cudaStream_t st, int trim = 0) {
   AttnParams ap;
   ap.trace = g_attn_trace;
   ap.trace_cap = g_attn_trace_cap;
@@ -831,6 +859,7 @@ int launch_attention(const CUtensorMap& qkv, const CUtensorMap& o_hi, const CUte
   ap.model_dim = kH;
   ap.kv_len = kv_len;
   ap.out_lo = out_lo;
+  ap.trim = trim && kv_len != nullptr;
   // experiment switches (profiles/r02_attention.md): SYL_ATTN_POLY = exp2 pairs (out of every four) computed on the
   // FMA pipe (0 or 1), SYL_ATTN_DEBUG = arithmetic-removal probes
 #ifdef SYL_DIAG
@@ -868,12 +897,13 @@ int run_frontend(syl_handle* h, const float* wav, cudaStream_t st) {
                at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift));
     __half* hi = at<__half>(ws, L.act_hi[0]);
     __half* lo = conv_split(h->mode, 1) ? at<__half>(ws, L.act_lo[0]) : nullptr;
+    const int32_t* needed0 = h->trim ? at<int32_t>(ws, L.valid) + B : nullptr;   // rows of conv0 the valid frames read
     if (lo)
       launch_pdl(conv0_mma_kernel<true>, dim3((L0 + C0M_T - 1) / C0M_T, B), dim3(C0M_THREADS), 0, st, wav, pl.t_samp, L0,
-                 h->conv0_bfrag, at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift), hi, lo);
+                 h->conv0_bfrag, at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift), hi, lo, needed0);
     else
       launch_pdl(conv0_mma_kernel<false>, dim3((L0 + C0M_T - 1) / C0M_T, B), dim3(C0M_THREADS), 0, st, wav, pl.t_samp, L0,
-                 h->conv0_bfrag, at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift), hi, lo);
+                 h->conv0_bfrag, at<float>(ws, L.gn_scale), at<float>(ws, L.gn_shift), hi, lo, needed0);
   }
   CUDA_TRY(h, cudaGetLastError());
   {
@@ -904,7 +934,7 @@ int run_layer(syl_handle* h, int l, float* h_out, cudaStream_t st) {
   }
   {
     StageTimer tm(h, ST_ATTN, st);
-    if (launch_attention(pl.attn_map, pl.ctx_hi_map, pl.ctx_lo_map, at<int32_t>(ws, L.valid), B, T, split_enc, h->sm_count, st))
+    if (launch_attention(pl.attn_map, pl.ctx_hi_map, pl.ctx_lo_map, at<int32_t>(ws, L.valid), B, T, split_enc, h->sm_count, st, h->trim))
       return fail(h, SYL_E_CUDA, "attention launch failed: %s", launch_err());
   }
   {
@@ -914,7 +944,8 @@ int run_layer(syl_handle* h, int l, float* h_out, cudaStream_t st) {
   {
     StageTimer tm(h, ST_LN_ENC, st);   // h = LN(h + attn); the residual stream is the fp16 pair (h16_hi, h16_lo), in place
     launch_ln<kH>(at<float>(ws, L.pre), nullptr, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo),
-                  w.ln1_g, w.ln1_b, M, nullptr, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), st);
+                  w.ln1_g, w.ln1_b, M, nullptr, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), st,
+                  h->trim ? at<int32_t>(ws, L.valid) : nullptr, T);
   }
   {
     StageTimer tm(h, ST_FFN1, st);
@@ -927,7 +958,8 @@ int run_layer(syl_handle* h, int l, float* h_out, cudaStream_t st) {
   {
     StageTimer tm(h, ST_LN_ENC, st);   // h = LN(h + ffn); fp32 only where the caller wants the layer output (h_out)
     launch_ln<kH>(at<float>(ws, L.pre), nullptr, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo),
-                  w.ln2_g, w.ln2_b, M, h_out, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), st);
+                  w.ln2_g, w.ln2_b, M, h_out, at<__half>(ws, L.h16_hi), at<__half>(ws, L.h16_lo), st,
+                  h->trim ? at<int32_t>(ws, L.valid) : nullptr, T);
   }
   CUDA_TRY(h, cudaGetLastError());
   return SYL_OK;
@@ -984,7 +1016,8 @@ int syl_create(syl_handle** out, int device, int n_layers, int mode) {
   h->n_layers = n_layers;
   if (mode & SYL_SPLIT_CONV) mode |= SYL_SPLIT_CONV2 | SYL_SPLIT_CONV3 | SYL_SPLIT_CONV4 | SYL_SPLIT_CONV5 | SYL_SPLIT_CONV6;
   if (mode & SYL_SPLIT_PROJ) mode |= SYL_SPLIT_FPROJ | SYL_SPLIT_POS;
-  h->mode = mode;
+  h->trim = (mode & SYL_TRIM_PADDING) != 0;
+  h->mode = mode & ~SYL_TRIM_PADDING;
   h->sm_count = prop.multiProcessorCount;
   *out = h;
   return SYL_OK;
@@ -1133,15 +1166,12 @@ static int enqueue_forward(syl_handle* h, Plan& pl, const float* wav, const int3
   const int T = L.T, M = batch * T;
   const bool split_proj = h->mode & SYL_SPLIT_FPROJ, split_enc = h->mode & SYL_SPLIT_ENC;
   int rc;
-  if (n_samples)
-    valid_frames_kernel<<<(batch + 127) / 128, 128, 0, st>>>(n_samples, batch, T, at<int32_t>(workspace, L.valid));
-  else
-    fill_i32_kernel<<<(batch + 127) / 128, 128, 0, st>>>(at<int32_t>(workspace, L.valid), batch, T);
+  valid_frames_kernel<<<(batch + 127) / 128, 128, 0, st>>>(n_samples, batch, T, at<int32_t>(workspace, L.valid));
   if ((rc = run_frontend(h, wav, st))) return rc;
   {
     StageTimer tm(h, ST_LN, st);
     launch_ln<kC>(at<float>(workspace, L.conv6), nullptr, nullptr, nullptr, h->fp_ln_g, h->fp_ln_b, M, nullptr, at<__half>(workspace, L.ln_hi),
-                  split_proj ? at<__half>(workspace, L.ln_lo) : nullptr, st);
+                  split_proj ? at<__half>(workspace, L.ln_lo) : nullptr, st, h->trim ? at<int32_t>(workspace, L.valid) : nullptr, T);
   }
   {
     StageTimer tm(h, ST_PROJ, st);
@@ -1156,7 +1186,8 @@ static int enqueue_forward(syl_handle* h, Plan& pl, const float* wav, const int3
   {
     StageTimer tm(h, ST_LN, st);
     launch_ln<kH>(at<float>(workspace, L.h), at<float>(workspace, L.pos), nullptr, nullptr, h->enc_ln_g, h->enc_ln_b, M,
-                  nl == 0 ? hidden : nullptr, at<__half>(workspace, L.h16_hi), at<__half>(workspace, L.h16_lo), st);
+                  nl == 0 ? hidden : nullptr, at<__half>(workspace, L.h16_hi), at<__half>(workspace, L.h16_lo), st,
+                  h->trim ? at<int32_t>(workspace, L.valid) : nullptr, T);
   }
   CUDA_TRY(h, cudaGetLastError());
   for (int l = 0; l < nl; ++l) {
@@ -1260,6 +1291,10 @@ int syl_conv_frontend(syl_handle* h, const float* wav, int batch, int t_samp_max
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int rc = build_plan(h, batch, t_samp_max, workspace, nullptr);
   if (rc) return rc;
+  {
+    const WsLayout& L0 = h->plans[h->plan_cur].lay;
+    valid_frames_kernel<<<(batch + 127) / 128, 128, 0, st>>>(nullptr, batch, L0.T, at<int32_t>(workspace, L0.valid));
+  }
   if ((rc = run_frontend(h, wav, st))) return rc;
   const WsLayout& L = h->plans[h->plan_cur].lay;
   CUDA_TRY(h, cudaMemcpyAsync(feats, at<float>(workspace, L.conv6), (size_t)batch * L.T * kC * sizeof(float),

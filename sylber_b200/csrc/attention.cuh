@@ -43,6 +43,7 @@ struct AttnParams {
   int model_dim;          // heads * 64
   const int* kv_len;      // [B] number of valid keys per utterance (== T when nothing is padded), or null
   int out_lo;             // also write the fp16 lo part through map o_lo
+  int trim;               // trimmed mode: query tiles at or beyond kv_len[b] (padded frames) are not computed
   int debug;              // timing experiments only (SYL_ATTN_DEBUG): 2 skip exp, 4 skip P store
   long long* trace;       // timeline probe (tools/attn_trace.py): CTA 0 logs clock64 stamps, 7 writers x trace_cap
   int trace_cap;
@@ -242,15 +243,17 @@ attention7_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_cons
   };
 
   // item -> (utterance, head, first query row, number of query tiles that hold at least one row < T)
+  auto item_kv_len = [&](int b) { return p.kv_len ? max(1, min(__ldg(p.kv_len + b), p.T)) : p.T; };
+  // n_act <= 0 (trimmed mode only): the whole item lies in the utterance's padding and every role skips it
   auto item_coords = [&](int item, int& b, int& h, int& q0, int& n_act) {
     const int grp = item % n_groups;
     const int bh = item / n_groups;
     h = bh % p.heads;
     b = bh / p.heads;
     q0 = grp * ATT_QT * ATT_BQ;
-    n_act = min(ATT_QT, q_tiles - grp * ATT_QT);
+    const int tiles_b = p.trim ? (item_kv_len(b) + ATT_BQ - 1) / ATT_BQ : q_tiles;
+    n_act = min(ATT_QT, tiles_b - grp * ATT_QT);
   };
-  auto item_kv_len = [&](int b) { return p.kv_len ? max(1, min(__ldg(p.kv_len + b), p.T)) : p.T; };
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
@@ -260,6 +263,7 @@ attention7_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_cons
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         int b, h, q0, n_act;
         item_coords(item, b, h, q0, n_act);
+        if (n_act <= 0) continue;
         const int n_blocks = (item_kv_len(b) + ATT_BKV - 1) / ATT_BKV;
 #pragma unroll
         for (int x = 0; x < ATT_QT; ++x) {
@@ -305,6 +309,7 @@ attention7_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_cons
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         int b, h, q0, n_act;
         item_coords(item, b, h, q0, n_act);
+        if (n_act <= 0) continue;
         const int U = (item_kv_len(b) + ATT_UNIT - 1) / ATT_UNIT;
         const int NB = (U + 1) >> 1;
         const int my_act = max(0, min(2, n_act - xa));

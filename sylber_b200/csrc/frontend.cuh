@@ -159,7 +159,7 @@ template <bool kLo>
 __global__ void __launch_bounds__(C0M_THREADS, 4)
 conv0_mma_kernel(const float* __restrict__ wav, int t_samp, int L0, const uint4* __restrict__ bfrag,
                  const float* __restrict__ scale, const float* __restrict__ shift, __half* __restrict__ out_hi,
-                 __half* __restrict__ out_lo) {
+                 __half* __restrict__ out_lo, const int32_t* __restrict__ needed_rows) {
   __shared__ float xs[C0M_T * C0_S + 16];
   __shared__ __align__(16) float s_sc[C0_OUT];
   __shared__ __align__(16) float s_sh[C0_OUT];
@@ -167,6 +167,7 @@ conv0_mma_kernel(const float* __restrict__ wav, int t_samp, int L0, const uint4*
   griddep_wait();
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * C0M_T;
+  if (needed_rows != nullptr && t0 >= __ldg(needed_rows + b)) return;   // trimmed mode: no valid frame reads these rows
   const int nt = min(C0M_T, L0 - t0);
   const float* w = wav + (size_t)b * t_samp + (size_t)t0 * C0_S;
   const int nsamp = nt * C0_S + (C0_K - C0_S);
@@ -257,13 +258,24 @@ template <int D>
 __global__ void __launch_bounds__(256, 4)
 layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ add, const __half* add_hi, const __half* add_lo,
                       const float* __restrict__ gamma, const float* __restrict__ beta, int rows, float* __restrict__ out_f32,
-                      __half* out_hi, __half* out_lo) {
+                      __half* out_hi, __half* out_lo, const int32_t* __restrict__ valid, int T) {
   constexpr int V = D / 128;  // float4 per lane
   griddep_launch_dependents();
   griddep_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = lane_id();
+  if (valid != nullptr && (row % T) >= __ldg(valid + row / T)) {
+    // trimmed mode: a padded frame.  Nothing upstream computed it; its outputs are defined as zero.
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const size_t o = (size_t)row * D + (size_t)(lane + 32 * i) * 4;
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (out_hi) *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(0u, 0u);
+      if (out_lo) *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(0u, 0u);
+    }
+    return;
+  }
   const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
   float4 v[V];
 #pragma unroll

@@ -80,6 +80,12 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
   griddep_wait();                            // the predecessor kernel's output (our A operand, valid_rows) is complete
+  // trimmed mode: every role skips the same tiles - those whose first row lies in an utterance's padding
+  auto tile_skipped = [&](int tile) -> bool {
+    if (!p.skip_invalid_tiles) return false;
+    const int m_tile = tile / tiles_n;
+    return (m_tile % tiles_m_per_batch) * 2 * GEMM_BLOCK_M >= __ldg(p.valid_rows + m_tile / tiles_m_per_batch);
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -87,6 +93,7 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        if (tile_skipped(tile)) continue;
         const int n_tile = tile % tiles_n;
         const int m_tile = tile / tiles_n;
         const int batch = m_tile / tiles_m_per_batch;
@@ -97,9 +104,14 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * GEMM2_STAGE_BYTES);   // bytes of BOTH CTAs' loads
-          tma_load_3d_2sm(smem_a + stage * GEMM2_A_BYTES, (pass == 1) ? &a_lo : &a_hi, full_leader,
+          // split precision: the two correction passes (A_lo B_hi, A_hi B_lo) come FIRST and A_hi B_hi last.  The tensor
+          // core adds each K = 16 step into the fp32 accumulator with truncation, i.e. a bias of ~half an ulp of the running
+          // sum per step (measured: conv1, 288 steps, 9.2e-6 relative = 288 x 3e-8, profiles/r03_precision.md); while the
+          // correction passes run the sum is 2^-11 of its final size, so only the last pass's steps cost a full ulp.
+          const bool a_is_lo = p.n_pass == 3 && pass == 0, b_is_lo = p.n_pass == 3 && pass == 1;
+          tma_load_3d_2sm(smem_a + stage * GEMM2_A_BYTES, a_is_lo ? &a_lo : &a_hi, full_leader,
                           kk * GEMM_BLOCK_K, row0, batch);
-          tma_load_2d_2sm(smem_b + stage * GEMM2_B_BYTES, (pass == 2) ? &b_lo : &b_hi, full_leader,
+          tma_load_2d_2sm(smem_b + stage * GEMM2_B_BYTES, b_is_lo ? &b_lo : &b_hi, full_leader,
                           kk * GEMM_BLOCK_K, n_tile * GEMM_BLOCK_N + (int)cta_rank * 128);
           if (++stage == GEMM2_STAGES) {
             stage = 0;
@@ -118,6 +130,7 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        if (tile_skipped(tile)) continue;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + acc * GEMM_BLOCK_N;
@@ -166,7 +179,8 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
       if (lane == 0) tma_store_wait_read();
       __syncwarp();
     };
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      if (tile_skipped(tile)) continue;
       const int n_tile = tile % tiles_n;
       const int m_tile = tile / tiles_n;
       const int batch = m_tile / tiles_m_per_batch;
@@ -278,6 +292,7 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
         acc = 0;
         acc_phase ^= 1;
       }
+      ++it;                                   // bias staging parity: counts processed tiles only
     }
     if (lane == 0) tma_store_wait_all();   // bulk stores must be complete before the CTA exits
   }

@@ -31,6 +31,7 @@ struct GemmParams {
   // epilogue
   const float* bias;        // [N] or null
   const int* valid_rows;    // [batches] or null: rows >= valid_rows[b] are written as zero
+  int skip_invalid_tiles;   // trimmed mode: 256-row tiles that start at or beyond valid_rows[b] are not computed at all
   int out_f32;              // write fp32 through map o_f32
   int out_hi;               // write fp16 hi through map o_hi
   int out_lo;               // write fp16 lo through map o_lo (requires out_hi)

@@ -403,6 +403,8 @@ class Segmenter:
       * extra keyword arguments: `state_dict=` (use these tensors instead of loading `model_ckpt`),
         `mode=` ("parity" default | "strict" | "fast" | "exact", see include/sylber_b200.h), `max_batch=`,
         `bucket_ratio=` (opt-in length-bucketed batching, batching.py), `thresholder=`,
+        `trim_padding=True` (opt-in: padded frames of short clips are not computed - their hidden rows are zeros and
+        carry no segments, the valid frames are unchanged; SYL_TRIM_PADDING in include/sylber_b200.h),
         `streams=` (sub-batches in flight, default 3: copies of one overlap kernels of the others).
     """
 
@@ -417,6 +419,7 @@ class Segmenter:
                  **kwargs):
         state_dict = kwargs.pop("state_dict", None)
         mode = kwargs.pop("mode", "parity")
+        self.trim_padding = bool(kwargs.pop("trim_padding", False))   # opt-in: do not compute padded frames (SYL_TRIM_PADDING)
         self.max_batch = int(kwargs.pop("max_batch", 64))
         self.streams = int(kwargs.pop("streams", 3))
         self.sub_batch_sizes = kwargs.pop("sub_batch_sizes", None)
@@ -443,7 +446,8 @@ class Segmenter:
 
         if 'cuda' in str(device) and not torch.cuda.is_available():
             raise RuntimeError("CUDA is not available and sylber_b200 has no CPU path")
-        self._engine = _Engine(state_dict, encoding_layer, device, mode)
+        mode_bits = (_lib.MODES[mode] if isinstance(mode, str) else int(mode)) | (_lib.SYL_TRIM_PADDING if self.trim_padding else 0)
+        self._engine = _Engine(state_dict, encoding_layer, device, mode_bits)
         self.speech_model = SpeechModel(self._engine)
         self.device = str(self._engine.device)
         self.norm_threshold = norm_threshold

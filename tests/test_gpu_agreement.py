@@ -31,8 +31,10 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOL = 1e-3
 MODES = ("parity", "fast", "exact")
-# fraction of utterances whose segments must equal the oracle's, per mode (measured floors, see the profiles table)
-MIN_AGREE = {"parity": 0.0, "fast": 0.0, "exact": 0.0}
+# fraction of utterances whose segments must equal the oracle's, per mode: floors below the measured rates of
+# profiles/r03_segment_agreement.md (parity 24/32, 9/16; fast 24/32, 8/16; exact 32/32, 15/16, 2/2), applied to the
+# configurations with at least 16 oracle rows (fast / parity) or to all of them (exact)
+MIN_AGREE = {"parity": 0.4, "fast": 0.35, "exact": 0.9}
 
 
 def _inputs(name):
@@ -114,6 +116,7 @@ def test_segments_against_oracle_at_metric_sizes(cuda, name, mode):
     with open(os.path.join(out_dir, f"{name}_{mode}.json"), "w") as f:
         json.dump({"summary": summ, "records": records}, f, indent=1, default=float)
     assert summ["all_flips_explained"], summ["flips"]
-    assert summ["agree"] >= MIN_AGREE[mode] * len(rows), summ
+    if mode == "exact" or len(rows) >= 16:
+        assert summ["agree"] >= MIN_AGREE[mode] * len(rows), summ
     del seg
     torch.cuda.empty_cache()
