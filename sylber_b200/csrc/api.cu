@@ -693,6 +693,8 @@ int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
     if (!h->plans[i].valid) { victim = i; break; }
     if (h->plans[i].last_use < h->plans[victim].last_use) victim = i;
   }
+  if (h->trim && batch > GEMM2_MAX_TRIM_BATCHES)
+    return fail(h, SYL_E_ARG, "trimmed mode handles at most %d utterances per call, got %d", GEMM2_MAX_TRIM_BATCHES, batch);
   h->plan_cur = victim;
   Plan& pl = h->plans[h->plan_cur];
   pl.valid = false;

@@ -29,7 +29,9 @@ constexpr int GEMM2_EPI_BYTES = 32768;                          // epilogue stag
 constexpr int GEMM2_SMEM_EPI = GEMM2_STAGES * GEMM2_STAGE_BYTES;
 constexpr int GEMM2_SMEM_BIAS = GEMM2_SMEM_EPI + GEMM2_EPI_BYTES;
 constexpr int GEMM2_SMEM_BAR = GEMM2_SMEM_BIAS + 2 * GEMM_BLOCK_N * 4;
-constexpr int GEMM2_SMEM_TOTAL = GEMM2_SMEM_BAR + 256;
+constexpr int GEMM2_SMEM_PREFIX = GEMM2_SMEM_BAR + 256;         // trimmed mode: prefix sums of computed M tiles per utterance
+constexpr int GEMM2_MAX_TRIM_BATCHES = 127;
+constexpr int GEMM2_SMEM_TOTAL = GEMM2_SMEM_PREFIX + (GEMM2_MAX_TRIM_BATCHES + 1) * 4;
 static_assert(GEMM2_SMEM_TOTAL <= 232448, "shared memory budget");
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {

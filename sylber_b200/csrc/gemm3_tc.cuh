@@ -80,11 +80,35 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
   griddep_wait();                            // the predecessor kernel's output (our A operand, valid_rows) is complete
-  // trimmed mode: every role skips the same tiles - those whose first row lies in an utterance's padding
-  auto tile_skipped = [&](int tile) -> bool {
-    if (!p.skip_invalid_tiles) return false;
-    const int m_tile = tile / tiles_n;
-    return (m_tile % tiles_m_per_batch) * 2 * GEMM_BLOCK_M >= __ldg(p.valid_rows + m_tile / tiles_m_per_batch);
+  // Trimmed mode (p.skip_invalid_tiles): M tiles that start in an utterance's padding are not computed.  The tile list
+  // every role walks is COMPACTED - cluster c takes the c-th, (c + C)-th, ... computed tile - so the persistent grid
+  // stays balanced however the valid lengths are distributed; m_prefix[b] = computed M tiles of utterances < b.
+  // (read after griddep_wait: valid_rows is written by a predecessor kernel)
+  int* m_prefix = reinterpret_cast<int*>(smem + GEMM2_SMEM_PREFIX);
+  const bool compact = p.skip_invalid_tiles != 0;
+  int total_tiles = num_tiles;
+  if (compact) {
+    if (threadIdx.x == 0) {
+      int acc_t = 0;
+      for (int bb = 0; bb < p.batches; ++bb) {
+        m_prefix[bb] = acc_t;
+        acc_t += min(tiles_m_per_batch, (max(__ldg(p.valid_rows + bb), 0) + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M));
+      }
+      m_prefix[p.batches] = acc_t;
+    }
+    __syncthreads();
+    total_tiles = m_prefix[p.batches] * tiles_n;
+  }
+  // tile index -> (utterance, M tile inside it); `cur` is the caller's monotonically advancing utterance cursor
+  auto decode_m = [&](int m_idx, int& cur, int& batch, int& m_in_batch) {
+    if (compact) {
+      while (m_idx >= m_prefix[cur + 1]) ++cur;
+      batch = cur;
+      m_in_batch = m_idx - m_prefix[cur];
+    } else {
+      batch = m_idx / tiles_m_per_batch;
+      m_in_batch = m_idx % tiles_m_per_batch;
+    }
   };
 
   if (warp == 0) {
@@ -92,12 +116,12 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        if (tile_skipped(tile)) continue;
+      int cur = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         const int n_tile = tile % tiles_n;
-        const int m_tile = tile / tiles_n;
-        const int batch = m_tile / tiles_m_per_batch;
-        const int row0 = (m_tile % tiles_m_per_batch) * 2 * GEMM_BLOCK_M + (int)cta_rank * GEMM_BLOCK_M;
+        int batch, m_in_batch;
+        decode_m(tile / tiles_n, cur, batch, m_in_batch);
+        const int row0 = m_in_batch * 2 * GEMM_BLOCK_M + (int)cta_rank * GEMM_BLOCK_M;
         for (int kb = 0; kb < kb_total; ++kb) {
           const int pass = kb / p.kb_per_pass;
           const int kk = kb - pass * p.kb_per_pass;
@@ -129,8 +153,7 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        if (tile_skipped(tile)) continue;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + acc * GEMM_BLOCK_N;
@@ -179,12 +202,12 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
       if (lane == 0) tma_store_wait_read();
       __syncwarp();
     };
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      if (tile_skipped(tile)) continue;
+    int cur = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       const int n_tile = tile % tiles_n;
-      const int m_tile = tile / tiles_n;
-      const int batch = m_tile / tiles_m_per_batch;
-      const int warp_row0 = (m_tile % tiles_m_per_batch) * 2 * GEMM_BLOCK_M + (int)cta_rank * GEMM_BLOCK_M + quarter * 32;
+      int batch, m_in_batch;
+      decode_m(tile / tiles_n, cur, batch, m_in_batch);
+      const int warp_row0 = m_in_batch * 2 * GEMM_BLOCK_M + (int)cta_rank * GEMM_BLOCK_M + quarter * 32;
       const int row_in_batch = warp_row0 + lane;
       const bool warp_ok = warp_row0 < p.rows_per_batch;
       const bool zero_row = p.valid_rows != nullptr && row_in_batch >= __ldg(p.valid_rows + batch);
