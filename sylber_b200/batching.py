@@ -42,10 +42,11 @@ def sub_batch_bounds(n_rows, streams=3, max_batch=64, explicit=None):
     """(lo, hi) bounds of the sub-batches one padded batch of `n_rows` rows is run as (Segmenter._run_jobs).
 
     A batch of at most `max_batch` rows is split over up to `streams` sub-batches (none smaller than 8 rows on
-    average) so that the copies of one overlap the kernels of the others; the LAST sub-batch gets 2/3 of an even
-    share because its device->host copy is the one nothing overlaps (32 rows, 3 streams -> 12, 12, 8: measured 6.08 ms
-    against 6.40 ms for 11, 11, 10).  Longer lists go through in `max_batch` chunks.  `explicit` (a list of sizes that
-    sums to n_rows) overrides the rule - used by tools/e2e_splits.py."""
+    average) so that the copies of one overlap the kernels of the others; the FIRST sub-batch gets 2/3 of an even
+    share because its host->device copy is the one nothing overlaps, while the last one's hidden states travel to
+    the host during its own segmentation scan (Segmenter._run_jobs).  32 rows, 3 streams -> 8, 12, 12: measured 6.01-6.05 ms
+    against 6.10 for 12, 12, 8 and 6.59 for 6, 10, 10, 6 (profiles/r03_e2e.md).  Longer lists go through in `max_batch`
+    chunks.  `explicit` (a list of sizes that sums to n_rows) overrides the rule - used by tools/e2e_splits.py."""
     if explicit and sum(explicit) == n_rows:
         out, a = [], 0
         for k in explicit:
@@ -58,7 +59,7 @@ def sub_batch_bounds(n_rows, streams=3, max_batch=64, explicit=None):
         hi = min(lo + max_batch, n_rows)
         n = hi - lo
         sizes = [int(round(n / (n_sub - 1 / 3)))] * (n_sub - 1) if n_sub > 1 else []
-        sizes.append(n - sum(sizes))
+        sizes.insert(0, n - sum(sizes))
         if min(sizes) <= 0:
             sizes = [n]
         a = lo

@@ -81,8 +81,10 @@ class _Engine:
         self.handle = handle
         self._workspaces = {}
         self._io = {}
+        self._seg_io = {}
         self._stage_in = {}
         self._streams = []
+        self._copy_streams = []
         self._resamplers = {}
         self.pool = _PinnedPool()
         missing = [k for k in REQUIRED_KEYS(n_layers) if k not in state_dict]
@@ -224,19 +226,34 @@ class _Engine:
         _lib.check(self.lib, None, rc, "syl_prepare_f32")
         return wav_dev, n_dev
 
-    def segment_states(self, states, thr_norm, thr_merge):
-        """get_segment + pooling on given (B,T,768) fp32 device states (syl_segment)."""
+    def segment_states(self, states, thr_norm, thr_merge, slot=None):
+        """get_segment + pooling on given (B,T,768) fp32 device states (syl_segment).  With `slot`, the outputs and the
+        workspace are persistent per (slot, B, T) - overwritten by the next call of the same slot and shape."""
         B, T, _ = states.shape
-        need = int(self.lib.syl_segment_workspace_bytes(B, T))
-        ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-        seg = torch.empty((B, T, 2), dtype=torch.int32, device=self.device)
-        cnt = torch.empty((B,), dtype=torch.int32, device=self.device)
-        feat = torch.empty((B, T, HIDDEN), dtype=torch.float32, device=self.device)
+        key = ("seg", slot, B, T)
+        bufs = self._seg_io.get(key) if slot is not None else None
+        if bufs is None:
+            need = int(self.lib.syl_segment_workspace_bytes(B, T))
+            bufs = (torch.empty(need, dtype=torch.uint8, device=self.device),
+                    torch.empty((B, T, 2), dtype=torch.int32, device=self.device),
+                    torch.empty((B,), dtype=torch.int32, device=self.device),
+                    torch.empty((B, T, HIDDEN), dtype=torch.float32, device=self.device))
+            if slot is not None:
+                while len(self._seg_io) >= 12:
+                    self._seg_io.pop(next(iter(self._seg_io)))
+                self._seg_io[key] = bufs
+        ws, seg, cnt, feat = bufs
         stream = torch.cuda.current_stream(self.device).cuda_stream
         rc = self.lib.syl_segment(_ptr(states), B, T, float(thr_norm), float(thr_merge), _ptr(seg), _ptr(cnt), _ptr(feat), T,
-                                  _ptr(ws), need, ctypes.c_void_p(stream))
+                                  _ptr(ws), ws.numel(), ctypes.c_void_p(stream))
         _lib.check(self.lib, None, rc, "syl_segment")
         return seg, cnt, feat
+
+    def copy_streams(self, n):
+        """One device->host copy stream per sub-batch slot: the hidden states travel while the segmentation still runs."""
+        while len(self._copy_streams) < n:
+            self._copy_streams.append(torch.cuda.Stream(device=self.device))
+        return self._copy_streams[:n]
 
     def stage_input(self, rows, max_length, slot=0, block=None):
         """Zero-padded (B, max_length) fp32 batch in a persistent pinned buffer (consumed within the call)."""
@@ -497,10 +514,12 @@ class Segmenter:
         thr_n, thr_m = np.float32(self.norm_threshold), np.float32(self.merge_threshold)
         results = [None] * len(rows)
 
+        copy_streams = eng.copy_streams(len(streams))
+
         def collect(item):
-            st, idx, hidden_h, hidden_pin, seg_pin, cnt_pin, feat, ev = item
+            st, cst, idx, hidden_h, hidden_pin, seg_pin, cnt_pin, feat, ev = item
             # the segment table travels first (it is tiny), so the number of segments is known on the host while the
-            # hidden states are still in flight and the feature copy queues right behind them: one wait, not three
+            # hidden states are still in flight and the feature copy queues right behind the table: one wait, not three
             ev.synchronize()
             cnt_h = cnt_pin.numpy()
             n_max = max(int(cnt_h.max()) if len(cnt_h) else 0, 1)
@@ -508,6 +527,7 @@ class Segmenter:
                 feat_h, feat_pin = eng.pool.array((len(idx), n_max, HIDDEN))
                 feat_pin.copy_(feat[:, :n_max], non_blocking=True)
             st.synchronize()
+            cst.synchronize()
             seg_h = seg_pin.numpy()
             del hidden_pin, feat_pin
             for i, r in enumerate(idx):
@@ -518,7 +538,7 @@ class Segmenter:
         pending = [None] * len(streams)                # per slot: the sub-batch whose buffers are still in use
         for k, (idx, max_length) in enumerate(work):
             slot = k % len(streams)
-            st = streams[slot]
+            st, cst = streams[slot], copy_streams[slot]
             if pending[slot] is not None:              # this slot's staging buffer, workspace and outputs are about to be reused
                 collect(pending[slot])
                 pending[slot] = None
@@ -530,7 +550,16 @@ class Segmenter:
                     wav_dev, n_dev = eng.upload_pcm16(chunk, sub_len, max_length, slot, pcm)
                 else:
                     wav_dev, n_dev = eng.upload(chunk, sub_len, max_length, slot)
-                hidden, seg, cnt, feat = eng.forward(wav_dev, n_dev, thr_n, thr_m, slot=slot)
+                # encoder first; its hidden states start their trip to the host on the slot's copy stream while the
+                # segmentation scan (latency bound, ~0.3 ms whatever the sub-batch size) and the pooling still run
+                hidden, _, _, _ = eng.forward(wav_dev, n_dev, thr_n, thr_m, segment=False, slot=slot)
+                ev_h = torch.cuda.Event()
+                ev_h.record(st)
+                cst.wait_event(ev_h)
+                with torch.cuda.stream(cst):
+                    hidden_h, hidden_pin = eng.pool.array(tuple(hidden.shape))
+                    hidden_pin.copy_(hidden, non_blocking=True)
+                seg, cnt, feat = eng.segment_states(hidden, thr_n, thr_m, slot=slot)
                 if tables is not None:
                     tables[0][idx[0]:idx[-1] + 1].copy_(seg, non_blocking=True)
                     tables[1][idx[0]:idx[-1] + 1].copy_(cnt, non_blocking=True)
@@ -540,9 +569,7 @@ class Segmenter:
                 seg_pin.copy_(seg, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(st)
-                hidden_h, hidden_pin = eng.pool.array(tuple(hidden.shape))
-                hidden_pin.copy_(hidden, non_blocking=True)
-            pending[slot] = (st, idx, hidden_h, hidden_pin, seg_pin, cnt_pin, feat, ev)
+            pending[slot] = (st, cst, idx, hidden_h, hidden_pin, seg_pin, cnt_pin, feat, ev)
         # collect in launch order: the oldest sub-batch finishes first
         n_w = len(work)
         for k in range(max(0, n_w - len(streams)), n_w):

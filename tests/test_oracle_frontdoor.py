@@ -129,11 +129,11 @@ def test_sub_batch_bounds_cover_every_row_once():
                 assert all(hi - lo <= max_batch for lo, hi in b)
                 if n <= max_batch:
                     assert len(b) <= streams
-    assert [hi - lo for lo, hi in sub_batch_bounds(32, 3, 32)] == [12, 12, 8]
+    assert [hi - lo for lo, hi in sub_batch_bounds(32, 3, 32)] == [8, 12, 12]
     assert [hi - lo for lo, hi in sub_batch_bounds(7, 3, 32)] == [7]
     assert [hi - lo for lo, hi in sub_batch_bounds(80, 3, 32)] == [32, 32, 16]
     assert sub_batch_bounds(32, 3, 32, explicit=[16, 16]) == [(0, 16), (16, 32)]
-    assert [hi - lo for lo, hi in sub_batch_bounds(32, 3, 32, explicit=[5, 5])] == [12, 12, 8]      # wrong sum: rule applies
+    assert [hi - lo for lo, hi in sub_batch_bounds(32, 3, 32, explicit=[5, 5])] == [8, 12, 12]      # wrong sum: rule applies
 
 
 def test_resampled_length_matches_ceil():

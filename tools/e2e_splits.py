@@ -2,12 +2,12 @@
 import sys, time, torch
 sys.path.insert(0, ".")
 from sylber_b200 import Segmenter
-from sylber_b200.weights import syllabic_test_state_dict
-sd = syllabic_test_state_dict(9, 0)
+from sylber_b200.weights import syllabic_test_state_dict, SPEECH_LIKE_BIAS_NORM
+sd = syllabic_test_state_dict(9, 0, SPEECH_LIKE_BIAS_NORM)
 g = torch.Generator().manual_seed(1)
 wav = torch.randn(32, 160000, generator=g).pin_memory()
 wl = [wav[i:i+1] for i in range(32)]
-for split in ([32], [16, 16], [11, 11, 10], [12, 12, 8], [14, 12, 6], [13, 10, 9], [8, 8, 8, 8], [10, 8, 8, 6], [12, 10, 6, 4], [16, 10, 6]):
+for split in ([11, 11, 10], [12, 12, 8], [14, 12, 6], [8, 12, 12], [6, 10, 10, 6]):
     seg = Segmenter(model_ckpt=None, state_dict=sd, device="cuda:0", streams=len(split), sub_batch_sizes=split, max_batch=32)
     for _ in range(4): seg(wav=wl)
     torch.cuda.synchronize(); t0 = time.perf_counter()
