@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from sylber_b200 import _lib
 import gpu_util as G
-lib = _lib.load_library()
+lib = _lib.load_diag_library() if os.environ.get("SYL_DIAG_LIB") == "1" else _lib.load_library()
 dev = torch.device("cuda", 0)
 for (B, T) in [(32, 499), (8, 2999)]:
     qkv = (torch.randn(B * T, 2304, device=dev) * 0.5).half()
