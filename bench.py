@@ -363,19 +363,17 @@ def run_ours(args):
         n_dev = torch.tensor(lens[lo:hi], dtype=torch.int32, device=dev)
         subs.append((wav_dev, n_dev))
     per_rank = B
-    gathered_cnt = torch.empty((world * per_rank,), dtype=torch.int32, device=dev) if world > 1 else None
-    gathered_seg = torch.empty((world * per_rank, T, 2), dtype=torch.int32, device=dev) if world > 1 else None
+    # the one exchange of the path: (count, fixed-stride segment table) of every utterance as ONE (B, 1 + T, 2) int32 block
+    gathered = torch.empty((world * per_rank, 1 + T, 2), dtype=torch.int32, device=dev) if world > 1 else None
 
     run_stream = torch.cuda.Stream(device=dev)      # a real stream: the library replays its CUDA graph on it
     torch.cuda.set_stream(run_stream)
 
     def step():
         outs = [eng.forward(w, n, thr_n, thr_m, slot=("bench", k)) for k, (w, n) in enumerate(subs)]
-        if world > 1:  # the one exchange of the path: the fixed-stride segment table
-            cnt = torch.cat([o[2] for o in outs]) if len(outs) > 1 else outs[0][2]
-            sg = torch.cat([o[1] for o in outs]) if len(outs) > 1 else outs[0][1]
-            dist.all_gather_into_tensor(gathered_cnt, cnt)
-            dist.all_gather_into_tensor(gathered_seg, sg)
+        if world > 1:  # the fixed-stride segment table, count in row 0: one all-gather over NCCL / NVSwitch
+            block = torch.cat([torch.cat([o[2].view(-1, 1, 1).expand(-1, 1, 2), o[1]], dim=1) for o in outs])
+            dist.all_gather_into_tensor(gathered, block)
         return outs
 
     def barrier():

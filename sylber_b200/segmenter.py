@@ -178,18 +178,22 @@ class _Engine:
         return ent
 
     def upload_pcm16(self, rows, lengths, max_length, slot, sample_rate=16000):
-        """int16 PCM rows -> the slot's (B, max_length) fp32 device batch, converted, (resampled,) z-normalised and
-        zero padded on the GPU (syl_prepare_pcm16 / syl_resample / syl_prepare_f32; sylber.py:83-87 + :93-118).
-        The samples travel back to back as int16.  `lengths` / `max_length` count 16 kHz samples."""
+        """Raw audio rows -> the slot's (B, max_length) fp32 device batch, converted, (resampled,) z-normalised and zero
+        padded on the GPU (syl_prepare_pcm16 / syl_resample / syl_prepare_f32; sylber.py:83-87 + :93-118).
+        Rows are int16 PCM (they travel back to back as int16: half the host->device bytes) or float32 samples in
+        [-1, 1) as an audio file reader returns them (the reference's file branch).  `lengths` / `max_length` count
+        16 kHz samples."""
         B = len(rows)
+        is_f32 = rows[0].dtype == torch.float32
         in_len = [int(r.shape[-1]) for r in rows]
         total = sum(in_len)
-        key = ("pcm", slot)
+        key = ("raw_f32" if is_f32 else "pcm", slot)
         buf = self._stage_in.get(key)
         if buf is None or buf[0].numel() < total or buf[2].numel() < B:
             cap = max(total, 1)
-            buf = self._stage_in[key] = (torch.empty(cap, dtype=torch.int16, pin_memory=True),
-                                         torch.empty(cap, dtype=torch.int16, device=self.device),
+            dt = torch.float32 if is_f32 else torch.int16
+            buf = self._stage_in[key] = (torch.empty(cap, dtype=dt, pin_memory=True),
+                                         torch.empty(cap, dtype=dt, device=self.device),
                                          torch.empty(max(B, 64), dtype=torch.int64, device=self.device))
         host, dev, off_dev = buf
         offsets, o = [], 0
@@ -207,17 +211,18 @@ class _Engine:
         if ws is None or ws.numel() < need:
             ws = self._stage_in[("pcm_ws", slot)] = torch.empty(need, dtype=torch.uint8, device=self.device)
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        prepare = self.lib.syl_prepare_f32 if is_f32 else self.lib.syl_prepare_pcm16
+        pname = "syl_prepare_f32" if is_f32 else "syl_prepare_pcm16"
         if sample_rate == 16000:
-            rc = self.lib.syl_prepare_pcm16(_ptr(dev), _ptr(off_dev), _ptr(n_dev), B, max_length, 1, _ptr(wav_dev), _ptr(ws), need,
-                                            stream)
-            _lib.check(self.lib, None, rc, "syl_prepare_pcm16")
+            rc = prepare(_ptr(dev), _ptr(off_dev), _ptr(n_dev), B, max_length, 1, _ptr(wav_dev), _ptr(ws), need, stream)
+            _lib.check(self.lib, None, rc, pname)
             return wav_dev, n_dev
-        # other rates (sylber.py:84-86): int16 -> fp32, sinc resampling to 16 kHz, then (w - mean) / std - all on the device
+        # other rates (sylber.py:84-86): -> fp32 rows, sinc resampling to 16 kHz, then (w - mean) / std - all on the device
         kern, width, orig_g, new_g = self._resampler(sample_rate)
         n_in = torch.tensor(in_len, dtype=torch.int32).to(self.device, non_blocking=True)
         raw = torch.empty((B, t_in), dtype=torch.float32, device=self.device)
-        rc = self.lib.syl_prepare_pcm16(_ptr(dev), _ptr(off_dev), _ptr(n_in), B, t_in, 0, _ptr(raw), _ptr(ws), need, stream)
-        _lib.check(self.lib, None, rc, "syl_prepare_pcm16")
+        rc = prepare(_ptr(dev), _ptr(off_dev), _ptr(n_in), B, t_in, 0, _ptr(raw), _ptr(ws), need, stream)
+        _lib.check(self.lib, None, rc, pname)
         res = torch.empty((B, max_length), dtype=torch.float32, device=self.device)
         rc = self.lib.syl_resample(_ptr(raw), _ptr(n_in), B, t_in, _ptr(kern), orig_g, new_g, width, _ptr(res), None, max_length, stream)
         _lib.check(self.lib, None, rc, "syl_resample")
@@ -489,6 +494,21 @@ class Segmenter:
             batch_wavs = wav if is_batch else [wav]
         return batch_wavs, is_batch
 
+    @staticmethod
+    def _read_files_raw(wav_file):
+        """File branch with the preprocessing left to the GPU: (raw fp32 rows, common sample rate, is_batch), or None when
+        the files do not share one sample rate or are not mono (the reference normalises all channels of a file jointly,
+        sylber.py:86) - those go through `_prepare` on the host."""
+        is_batch = isinstance(wav_file, list)
+        rows, rate = [], None
+        for file in (wav_file if is_batch else [wav_file]):
+            w, sr = _read_audio(os.fspath(file))
+            if w.dim() != 2 or w.shape[0] != 1 or (rate is not None and sr != rate):
+                return None
+            rate = sr
+            rows.append(w[0].contiguous())
+        return rows, rate, is_batch
+
     # ------------------------------------------------------------------------------------------
     def _sub_batches(self, n_rows):
         """(lo, hi) sub-batch bounds of one padded batch of n_rows rows (batching.sub_batch_bounds)."""
@@ -601,7 +621,11 @@ class Segmenter:
                     for x in (pcm16 if is_batch else [pcm16])]
             if any(r.dtype != torch.int16 for r in rows):
                 raise TypeError("pcm16 expects int16 samples")
-        else:
+        raw_files = self._read_files_raw(wav_file) if (wav_file is not None and not pcm) else None
+        if raw_files is not None:
+            # the reference's file branch (sylber.py:83-87) with resampling, (w - mean) / std and padding on the GPU
+            rows, pcm, is_batch = raw_files
+        elif not pcm:
             batch_wavs, is_batch = self._prepare(wav_file, wav)
             rows = []
             for w in batch_wavs:
@@ -714,7 +738,9 @@ class KMeansQuantizer:
 
     @torch.no_grad()
     def get_indices(self, token, return_distance=False):
-        """token (..., 768) array or tensor -> int64 indices of shape token.shape[:-1] (quantizer.py:95-106)."""
+        """token (..., 768) array or tensor -> int64 indices of shape token.shape[:-1] + (1,): the reference returns
+        `indices[0]` of a GroupedResidualVQ with one quantizer, i.e. a trailing quantizer axis of length 1
+        (quantizer.py:95-106), and its callers index it."""
         t = torch.as_tensor(token)
         lead = tuple(t.shape[:-1])
         x = t.reshape(-1, HIDDEN).to(device=self.device, dtype=torch.float32).contiguous()
@@ -726,9 +752,13 @@ class KMeansQuantizer:
             rc = self.lib.syl_kmeans_assign(_ptr(x), n, _ptr(self.centroids), self.centroids.shape[0], int(self.normalize),
                                             _ptr(idx), _ptr(dist), ctypes.c_void_p(stream))
         _lib.check(self.lib, None, rc, "syl_kmeans_assign")
-        out = idx.to(torch.int64).reshape(lead)
+        out = idx.to(torch.int64).reshape(lead + (1,))
         return (out, dist.reshape(lead)) if return_distance else out
 
     def decode(self, indices):
-        """quantizer.py:123-129: centroids of the given indices (negative indices clipped to 0)."""
-        return self.centroids[torch.as_tensor(indices, device=self.device).clip(0).long()]
+        """quantizer.py:123-129: centroids of `indices[..., :1]` (negative indices clipped to 0) -> (..., 768).
+        Accepts the (..., 1) layout get_indices returns as well as plain (...) index arrays."""
+        idx = torch.as_tensor(indices, device=self.device)
+        if idx.dim() >= 1 and idx.shape[-1] == 1:
+            idx = idx[..., 0]
+        return self.centroids[idx.clip(0).long()]

@@ -81,15 +81,18 @@ def test_kmeans_assign_vs_oracle(n, K, normalize):
     q = KMeansQuantizer(cent, normalize=normalize)
     idx, dist = q.get_indices(x.reshape(n, 768), return_distance=True)
     want, d = frontdoor_ref.kmeans_assign(x, cent, normalize=normalize)
-    idx = idx.cpu().numpy()
+    assert idx.shape == (n, 1)                                  # trailing quantizer axis, as the reference's indices[0]
+    idx = idx[:, 0].cpu().numpy()
     dmin = d.min(-1)
     chosen = d[np.arange(n), idx]
     assert np.all(chosen <= dmin * (1 + 1e-5) + 1e-4)          # identical except at numerical ties
     assert (idx == want).mean() >= 0.99
     assert np.allclose(dist.cpu().numpy(), chosen, rtol=1e-4, atol=1e-3)
-    assert q.get_indices(x.reshape(1, n, 768)).shape == (1, n)
+    tok = q.get_indices(x.reshape(1, n, 768))
+    assert tok.shape == (1, n, 1)
+    assert torch.equal(q.decode(tok).cpu(), torch.from_numpy(cent[tok[..., 0].cpu().numpy()]))     # decode slices [..., :1]
     assert torch.equal(q.decode(torch.tensor([0, -1])).cpu(), torch.from_numpy(cent[[0, 0]]))
-    assert q.get_indices(np.zeros((0, 768), np.float32)).shape == (0,)
+    assert q.get_indices(np.zeros((0, 768), np.float32)).shape == (0, 1)
 
 
 def test_sylber_segment_contract_on_given_features(seg9):
@@ -190,3 +193,30 @@ def test_segmenter_pcm16_other_sample_rate(seg9):
     for x, y in zip(a, b):
         assert x["hidden_states"].shape == y["hidden_states"].shape
         assert _rel(x["hidden_states"], y["hidden_states"]) < 5e-4
+
+
+@pytest.mark.parametrize("rate", [16000, 22050])
+def test_wav_file_branch_runs_its_preprocessing_on_the_device(seg9, tmp_path, rate):
+    """`Segmenter(wav_file)` - the reference's file branch (sylber.py:83-87): read, resample to 16 kHz, (w - mean) / std.
+    Mono files of one sample rate keep only the file read on the host; the rest is the device front door, so the result
+    is bit-identical to the `pcm16=` call on the same samples, and within the path's own error of the host-normalised
+    `wav=` call."""
+    from scipy.io import wavfile
+    rng = np.random.default_rng(11)
+    clips = [_pcm(rng, n) for n in (rate * 2, rate + 1234)]
+    paths = []
+    for i, c in enumerate(clips):
+        path = tmp_path / f"clip{i}.wav"
+        wavfile.write(str(path), rate, c)
+        paths.append(str(path))
+    a = seg9(wav_file=paths, in_second=False)
+    b = seg9(pcm16=clips, sample_rate=rate, in_second=False)
+    want_wav, lens = frontdoor_ref.normalize_pcm16(clips, sample_rate=rate)
+    c = seg9(wav=[want_wav[i:i + 1, :lens[i]] for i in range(2)], in_second=False)
+    assert isinstance(a, list) and len(a) == 2
+    for x, y, z in zip(a, b, c):
+        assert np.array_equal(x["hidden_states"], y["hidden_states"])
+        assert np.array_equal(np.asarray(x["segments"]), np.asarray(y["segments"]))
+        assert _rel(x["hidden_states"], z["hidden_states"]) < 5e-4
+    single = seg9(paths[0])                      # first positional argument is a path, dict out (sylber.py:63,138)
+    assert isinstance(single, dict) and np.array_equal(single["hidden_states"][:10], seg9(pcm16=clips[0], sample_rate=rate)["hidden_states"][:10])
