@@ -347,7 +347,7 @@ struct syl_handle {
   int device = 0;
   int n_layers = 9;
   int active_layers = -1;
-  int mode = SYL_MODE_PARITY;
+  int mode = SYL_MODE_FAST;
   bool trim = false;      // SYL_TRIM_PADDING: padded frames are not computed (opt-in deviation, include/sylber_b200.h)
   bool finalized = false;
   std::string err;

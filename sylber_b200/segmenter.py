@@ -423,7 +423,7 @@ class Segmenter:
         (the reference's fallback at :56-58 runs after `.to(device)` has already raised).
       * missing checkpoint tensors raise (the reference's strict=False at :52 ignores them).
       * extra keyword arguments: `state_dict=` (use these tensors instead of loading `model_ckpt`),
-        `mode=` ("parity" default | "strict" | "fast" | "exact", see include/sylber_b200.h), `max_batch=`,
+        `mode=` ("fast" default | "parity" | "strict" | "exact", see include/sylber_b200.h), `max_batch=`,
         `bucket_ratio=` (opt-in length-bucketed batching, batching.py), `thresholder=`,
         `trim_padding=True` (opt-in: padded frames of short clips are not computed - their hidden rows are zeros and
         carry no segments, the valid frames are unchanged; SYL_TRIM_PADDING in include/sylber_b200.h),
@@ -440,7 +440,7 @@ class Segmenter:
                  device='cuda',
                  **kwargs):
         state_dict = kwargs.pop("state_dict", None)
-        mode = kwargs.pop("mode", "parity")
+        mode = kwargs.pop("mode", "fast")
         self.trim_padding = bool(kwargs.pop("trim_padding", False))   # opt-in: do not compute padded frames (SYL_TRIM_PADDING)
         self.max_batch = int(kwargs.pop("max_batch", 64))
         self.streams = int(kwargs.pop("streams", 3))

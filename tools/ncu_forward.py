@@ -5,9 +5,9 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from sylber_b200 import Segmenter
-from sylber_b200.weights import syllabic_test_state_dict
-mode = sys.argv[1] if len(sys.argv) > 1 else "parity"
-seg = Segmenter(model_ckpt=None, state_dict=syllabic_test_state_dict(9, 0), device="cuda:0", mode=mode)
+from sylber_b200.weights import syllabic_test_state_dict, SPEECH_LIKE_BIAS_NORM
+mode = sys.argv[1] if len(sys.argv) > 1 else "fast"
+seg = Segmenter(model_ckpt=None, state_dict=syllabic_test_state_dict(9, 0, SPEECH_LIKE_BIAS_NORM), device="cuda:0", mode=mode)
 eng = seg._engine
 eng.lib.syl_set_graph_mode(eng.handle, 0)
 g = torch.Generator().manual_seed(1)
