@@ -59,11 +59,11 @@ typedef struct syl_handle syl_handle;
 #define SYL_SPLIT_FPROJ 512
 #define SYL_SPLIT_POS 1024
 /* Presets.  Measured on B200 against the fp32 CPU oracle (relative Frobenius error of the final hidden states, bar
- * 1e-3; device ms per step of batch 32 x 10 s; clips of that batch whose SEGMENTS equal the fp32 reference's,
- * profiles/r03_segment_agreement.md): fast 5.1e-4 / 4.8 ms / 24 of 32; parity 4.1e-4 / 5.1 ms / 24 of 32; strict
- * 3.0e-4 / 7.5 ms; exact 1.6e-5 / 10.9 ms / 32 of 32.  FAST is the default since round 3: the split of conv4-6 and
- * the projection moved the state error by 1e-4 but not one segment decision.  EXACT is the preset for segment
- * identity with the fp32 reference. */
+ * 1e-3; device ms per step of batch 32 x 10 s; clips whose SEGMENTS equal the fp32 reference's on configs 2 / 5,
+ * profiles/r03_segment_agreement.md): fast 5.1e-4 / 4.9 ms / 24 of 32, 8 of 16; parity 4.1e-4 / 5.1 ms / 27 of 32,
+ * 10 of 16; strict 3.0e-4 / 7.5 ms; exact 1.2e-5 / 10.9 ms / 32 of 32, 16 of 16.  FAST is the default since round 3:
+ * splitting conv4-6 and the projection costs 6 % of the step for 1e-4 of state error and a handful of threshold
+ * decisions, and both sit at half the tolerance.  EXACT is the preset for segment identity with the fp32 reference. */
 #define SYL_MODE_FAST 0                                                      /* single-pass fp16 everywhere (default) */
 #define SYL_MODE_PARITY (SYL_SPLIT_CONV4 | SYL_SPLIT_CONV5 | SYL_SPLIT_CONV6 | SYL_SPLIT_FPROJ)
 #define SYL_MODE_STRICT (SYL_SPLIT_CONV | SYL_SPLIT_CONV1 | SYL_SPLIT_PROJ)  /* whole front end split */
