@@ -78,6 +78,27 @@ def stage_flops(n_samples, layers):
     }, T, L
 
 
+def gemm_algorithmic_bytes(B, L, T, layers, mode):
+    """Algorithmic DRAM bytes of all gemm3_tc_kernel launches of one step (operands read once, outputs written once):
+    fp16 operands are 2 bytes, 4 where the site runs split (hi + lo), fp32 outputs 4 bytes."""
+    sc = set(SPLIT_CONV[mode])
+    s_proj = 2 if mode in ("parity", "strict", "exact") else 1
+    s_pos = 2 if mode in ("strict", "exact") else 1
+    s_enc = 2 if mode == "exact" else 1
+    M = B * T
+    total = 0
+    for i, k in zip(range(1, 7), (3, 3, 3, 3, 2, 2)):
+        s_in = 2 if i in sc else 1
+        total += B * L[i - 1] * 512 * 2 * s_in + 512 * 512 * k * 2 * s_in
+        total += B * L[i] * 512 * (4 if i == 6 else 2 * (2 if (i + 1) in sc else 1))
+    total += M * 512 * 2 * s_proj + 768 * 512 * 2 * s_proj + M * 768 * (4 + 2 * s_pos)
+    per_layer = (M * 768 * 2 * s_enc + 2304 * 768 * 2 * s_enc + M * 2304 * 2          # QKV
+                 + M * 768 * 2 * s_enc + 768 * 768 * 2 * s_enc + M * 768 * 4           # out-projection
+                 + M * 768 * 2 * s_enc + 3072 * 768 * 2 * s_enc + M * 3072 * 2 * s_enc  # FFN1
+                 + M * 3072 * 2 * s_enc + 768 * 3072 * 2 * s_enc + M * 768 * 4)         # FFN2
+    return total + layers * per_layer
+
+
 GEMM_STAGES = ("conv1_gemm", "conv2_6_gemm", "feature_proj_gemm", "qkv_gemm", "out_proj_gemm", "ffn1_gemm", "ffn2_gemm")
 ENC_STAGES = ("qkv_gemm", "attention", "out_proj_gemm", "ffn1_gemm", "ffn2_gemm")
 
@@ -499,7 +520,8 @@ def run_ours(args):
     if os.path.exists(tpath) and args.workload == "10s" and args.mode == "fast" and layers == 9:
         tj = json.load(open(tpath))
         ent = tj.get("gemm3_tc_kernel.all_launches") or {}
-        traffic, alg_bytes, tsrc = ent.get("dram_bytes_per_launch_mean"), ent.get("algorithmic_bytes_per_launch_mean"), ent.get("source")
+        traffic, tsrc = ent.get("dram_bytes_per_launch_mean"), ent.get("source")
+    alg_bytes = gemm_algorithmic_bytes(B, L, T, layers, args.mode) / n_launch
     enc_tf, enc_ms, _ = tf_of(ENC_STAGES)
     enc_ln_ms = stages.get("layernorm_encoder", {}).get("ms_per_step", 0.0)
     encln_tf, encln_ms, _ = tf_of(ENC_STAGES, enc_ln_ms)
