@@ -262,9 +262,7 @@ layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ add
   constexpr int V = D / 128;  // float4 per lane
   griddep_launch_dependents();
   griddep_wait();
-  // Blocks walk the rows from the END of the matrix: the producing GEMM wrote the highest rows last (they are the ones
-  // still in L2), and the consuming GEMM starts at row 0, which this order writes last (profiles/r03_bench_ab.md).
-  const int row = (gridDim.x - 1 - blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = lane_id();
   if (valid != nullptr && (row % T) >= __ldg(valid + row / T)) {
