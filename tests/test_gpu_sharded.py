@@ -93,3 +93,25 @@ def test_sharded_call_is_bit_identical_to_the_single_call(cuda, world, kind):
             else:
                 assert hid is None
             assert np.array_equal(res_local[i], want * 1.0 / 50 if len(want) else want)   # per-rank input lists, seconds
+
+
+def test_two_devices_in_one_process(cuda):
+    """the >48 KB shared-memory opt-in is per device, and entry points must not move the caller's current
+    device.  Two Segmenters on two GPUs of ONE process give identical results and leave torch's current device alone."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    from sylber_b200 import Segmenter
+    from sylber_b200.weights import syllabic_test_state_dict, SPEECH_LIKE_BIAS_NORM
+    sd = syllabic_test_state_dict(9, 0, SPEECH_LIKE_BIAS_NORM)
+    clips = _clips("mixed")[:3]
+    assert torch.cuda.current_device() == 0
+    a = Segmenter(model_ckpt=None, state_dict=sd, device="cuda:0")
+    b = Segmenter(model_ckpt=None, state_dict=sd, device="cuda:1")      # second handle, other device: needs its own attributes
+    assert torch.cuda.current_device() == 0
+    ra = a(wav=clips, in_second=False)
+    rb = b(wav=clips, in_second=False)
+    assert torch.cuda.current_device() == 0
+    ra2 = a(wav=clips, in_second=False)                                  # and back on device 0 after device 1 was used
+    for x, y, z in zip(ra, rb, ra2):
+        assert np.array_equal(x["hidden_states"], y["hidden_states"]) and np.array_equal(x["hidden_states"], z["hidden_states"])
+        assert np.array_equal(np.asarray(x["segments"]), np.asarray(y["segments"]))
