@@ -346,7 +346,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     affinity = None
-    if world > 1 and hasattr(os, "sched_setaffinity"):
+    if world > 1 and hasattr(os, "sched_setaffinity") and not args.no_affinity:
         # one process per GPU on one host: give every rank its own share of the host cores, so that the ranks' launch /
         # packaging threads do not migrate over each other (measured: e2e at 4 ranks, profiles/r03_multi_gpu.md)
         cores = sorted(os.sched_getaffinity(0))
@@ -451,7 +451,7 @@ def run_ours(args):
     # ---------------- end-to-end through the public call, from pinned host tensors to NumPy results ----------------
     def e2e_call():
         if world > 1:   # product-level sharded call: local forward + all-gather of the segment table on every step
-            return segment_sharded(seg, wav=clips, in_second=True, local_input=True, pad_to=pad_to)
+            return segment_sharded(seg, wav=clips, in_second=True, local_input=True, pad_to=pad_to, per_rank=B)
         return seg(wav=clips, in_second=True, pad_to=pad_to)
 
     for _ in range(3):
@@ -462,6 +462,18 @@ def run_ours(args):
         res = e2e_call()
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_local_s = None
+    if world > 1:
+        # the same call without the exchange (every rank only its own clips): separates the collective + straggler cost
+        # from what N processes sharing one host cost each other
+        for _ in range(2):
+            seg(wav=clips, in_second=True, pad_to=pad_to)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            seg(wav=clips, in_second=True, pad_to=pad_to)
+        torch.cuda.synchronize()
+        e2e_local_s = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop() if rank == 0 else None
     e2e_value = frames_valid * args.steps / e2e_s
     mine = res[rank * B:(rank + 1) * B] if world > 1 else res
@@ -570,7 +582,8 @@ def run_ours(args):
                    "e2e_input": f"list of {B} (1, n) fp32 views of pinned host memory"
                                 + ("; e2e = segment_sharded(local_input=True): forward + all-gather of counts and segment table" if world > 1 else "")},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_s / args.steps * 1e3},
+                "ms_per_step": e2e_s / args.steps * 1e3,
+                **({"ms_per_step_without_the_all_gather": e2e_local_s / args.steps * 1e3} if e2e_local_s else {})},
         "gpu_launches": eng.launch_count(True) * len(subs) * args.steps,
         "clocks": clocks,
         "roofline": roofline,
@@ -624,6 +637,7 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["parity", "strict", "fast", "exact"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / segment_agreement leg")
     ap.add_argument("--library-baseline", action="store_true", help="also time transformers.HubertModel eager on the GPU")
+    ap.add_argument("--no-affinity", action="store_true", help="N > 1: do not pin the ranks to disjoint host-core sets")
     ap.add_argument("--trim", action="store_true", help="trimmed mode: padded frames are not computed (opt-in deviation)")
     ap.add_argument("--streams", type=int, default=0, help="sub-batches in flight in the e2e leg (0 = Segmenter default)")
     ap.add_argument("--workload", default="10s", choices=["10s", "60s", "mixed"],

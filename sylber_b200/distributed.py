@@ -60,6 +60,9 @@ def unpack_segment_table(all_seg, all_cnt, n_items, world):
     return out
 
 
+LAST_TIMING = {}     # host-side phase times of the most recent segment_sharded fast-path call (tools/shard_probe.py)
+
+
 def _comm_device(segmenter, group):
     """NCCL moves device tensors, every other backend (gloo in the CPU tests) host tensors."""
     backend = dist.get_backend(group)
@@ -67,7 +70,7 @@ def _comm_device(segmenter, group):
 
 
 def segment_sharded(segmenter, wav_file=None, wav=None, in_second=True, group=None, local_input=False, pad_to=None,
-                    gather_features=False):
+                    gather_features=False, per_rank=None):
     """`Segmenter.__call__` for a LIST of utterances sharded over the ranks of `group` (one process per GPU).
 
     Every rank calls this collectively.  With `local_input=False` (default) every rank passes the same global list and
@@ -77,6 +80,10 @@ def segment_sharded(segmenter, wav_file=None, wav=None, in_second=True, group=No
     utterance's result depends on the padded length, so every rank pads to the T_max the single call
     would use - and (2) the segment table: an all-gather of the per-utterance segment counts, then of the fixed-stride
     (utterances, max count, 2) int32 table (a few KB over NCCL / NVSwitch).
+
+    `per_rank` (with `local_input=True`): an upper bound on the number of utterances any rank passes, known to the caller
+    (e.g. the per-GPU batch size).  It saves the collective that otherwise exchanges the list lengths on every call; the
+    actual lengths then travel inside the segment-table block.
 
     Returns the list of result dicts of the WHOLE batch in global order on every rank: `segments` for every utterance
     (bit-identical to what one process calling `segmenter(wav=whole_list)` returns - tests/test_gpu_sharded.py);
@@ -91,7 +98,14 @@ def segment_sharded(segmenter, wav_file=None, wav=None, in_second=True, group=No
         raise TypeError("segment_sharded shards a list of utterances; pass a list")
     items = list(items)
     dev = _comm_device(segmenter, group)
-    if local_input:
+    sizes_in_block = False
+    if local_input and per_rank is not None and hasattr(segmenter, "call_with_tables") and not gather_features:
+        if len(items) > per_rank:
+            raise ValueError(f"per_rank={per_rank} but this rank passes {len(items)} utterances")
+        sizes = None                      # read from the gathered block (header of every rank's first row)
+        sizes_in_block = True
+        mine = items
+    elif local_input:
         sizes = torch.zeros(world, dtype=torch.int64, device=dev)
         mine_n = torch.tensor([len(items)], dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(sizes, mine_n, group=group)
@@ -115,24 +129,58 @@ def segment_sharded(segmenter, wav_file=None, wav=None, in_second=True, group=No
         else:
             local_max = max((int(torch.as_tensor(w).shape[-1]) for w in local_kw["wav"]), default=0)
             pad_to = global_max_length(local_max, device=dev, group=group)
-    per_rank = max(sizes)
+    per_rank = int(per_rank) if sizes_in_block else max(sizes)
     all_feat_h = None
     if hasattr(segmenter, "call_with_tables") and not gather_features:
         # fast path: the device-side segment table goes into the collective as it is - ONE all-gather of a
         # (per_rank, 1 + T, 2) int32 block whose row 0 carries the count, then one device->host copy
-        T = segmenter._engine.num_frames(pad_to)
-        block = torch.zeros((per_rank, 1 + T, 2), dtype=torch.int32, device=segmenter._engine.device)
+        import time as _time
+        _t = [_time.perf_counter()]
+        eng = segmenter._engine
+        T = eng.num_frames(pad_to)
+        gdev = eng.device
+        block = torch.zeros((per_rank, 1 + T, 2), dtype=torch.int32, device=gdev)
+        comm = getattr(eng, "_comm_stream", None)
+        if comm is None:
+            comm = eng._comm_stream = torch.cuda.Stream(device=gdev)
+        state = {}
+
+        def exchange(streams, seg_dev, cnt_dev):
+            # enqueued behind the sub-batch streams while the host still waits for the last hidden states: fill the block,
+            # ONE all-gather, one copy of the gathered table into pinned memory
+            with torch.cuda.stream(comm):
+                for st in streams:
+                    comm.wait_stream(st)
+                if seg_dev is not None:
+                    block[:seg_dev.shape[0], 1:] = seg_dev
+                    block[:seg_dev.shape[0], 0, 0] = cnt_dev
+                    block[0, 0, 1] = seg_dev.shape[0]     # header: how many utterances this rank holds
+                src = block.to(dev)                       # gloo: host tensors (synchronises); NCCL: the device block itself
+                gathered = torch.empty((world * per_rank, 1 + T, 2), dtype=torch.int32, device=dev)
+                dist.all_gather_into_tensor(gathered, src, group=group)
+                if gathered.is_cuda:
+                    pin = torch.empty(gathered.shape, dtype=torch.int32, pin_memory=True)
+                    pin.copy_(gathered, non_blocking=True)
+                    state["ev"] = torch.cuda.Event()
+                    state["ev"].record(comm)
+                    state["g"] = pin
+                else:
+                    state["g"] = gathered
+
+        _t.append(_time.perf_counter())
         if mine:
-            local, seg_dev, cnt_dev = segmenter.call_with_tables(local_kw["wav"], pad_to=pad_to)
-            block[:len(mine), 1:] = seg_dev
-            block[:len(mine), 0, 0] = cnt_dev
+            local, _, _ = segmenter.call_with_tables(local_kw["wav"], pad_to=pad_to, after_enqueue=exchange)
         else:
             local = []
-        block = block.to(dev)
-        gathered = torch.empty((world * per_rank, 1 + T, 2), dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(gathered, block, group=group)
-        g = gathered.cpu().numpy()
+            exchange([], None, None)
+        _t.append(_time.perf_counter())
+        if "ev" in state:
+            state["ev"].synchronize()
+        _t.append(_time.perf_counter())
+        g = state["g"].numpy()
         all_cnt_h, all_seg_h = g[:, 0, 0], g[:, 1:]
+        if sizes_in_block:
+            sizes = [int(g[r * per_rank, 0, 1]) for r in range(world)]
     else:
         local = segmenter(in_second=False, pad_to=pad_to, **local_kw) if mine else []
         # (1) counts, (2) fixed-stride table
@@ -160,17 +208,27 @@ def segment_sharded(segmenter, wav_file=None, wav=None, in_second=True, group=No
             all_feat = torch.empty((world * per_rank, stride, 768), dtype=torch.float32, device=dev)
             dist.all_gather_into_tensor(all_feat, feat.to(dev), group=group)
             all_feat_h = all_feat.cpu().numpy()
+    # unpack: ONE int64 (and one seconds) conversion of the occupied part of the table, then per-utterance views - the loop
+    # runs over every utterance of the WHOLE batch on every rank, so it must not allocate or convert per row
+    counts = np.asarray(all_cnt_h).tolist()
+    n_max = max(max(counts), 1)
+    seg64 = np.ascontiguousarray(all_seg_h[:, :n_max], dtype=np.int64)
+    table = seg64 * 1.0 / 50 if in_second else seg64       # the reference's `segments * 1.0 / 50` (sylber.py:132)
+    empty = np.array([]) * 1.0 / 50 if in_second else np.array([])
     out = []
     for r in range(world):
+        base = r * per_rank
+        mine_r = r == rank
         for k in range(sizes[r]):
-            row = r * per_rank + k
-            n = int(all_cnt_h[row])
-            s = all_seg_h[row, :n].astype(np.int64) if n > 0 else np.array([])
-            d = {"segments": s * 1.0 / 50 if in_second else s, "segment_features": None, "hidden_states": None}
-            if r == rank:
+            n = counts[base + k]
+            d = {"segments": table[base + k, :n] if n > 0 else empty, "segment_features": None, "hidden_states": None}
+            if mine_r:
                 d["segment_features"] = local[k]["segment_features"]
                 d["hidden_states"] = local[k]["hidden_states"]
             elif all_feat_h is not None:
-                d["segment_features"] = all_feat_h[row, :n].copy() if n > 0 else np.array([])
+                d["segment_features"] = all_feat_h[base + k, :n] if n > 0 else np.array([])
             out.append(d)
+    if "_t" in locals():
+        _t.append(_time.perf_counter())
+        LAST_TIMING.update(setup=_t[1] - _t[0], call=_t[2] - _t[1], wait_gather=_t[3] - _t[2], unpack=_t[4] - _t[3])
     return out

@@ -514,12 +514,14 @@ class Segmenter:
         """(lo, hi) sub-batch bounds of one padded batch of n_rows rows (batching.sub_batch_bounds)."""
         return sub_batch_bounds(n_rows, self.streams, self.max_batch, self.sub_batch_sizes)
 
-    def _run_jobs(self, rows, lengths, jobs, pcm=0, tables=None):
+    def _run_jobs(self, rows, lengths, jobs, pcm=0, tables=None, after_enqueue=None):
         """Padded batches through the engine.  rows: 1-D fp32 CPU tensors (or int16 at `pcm` Hz when pcm != 0); jobs: list of
         (row indices, max_length) - every row of a job is padded to that job's max_length (results depend on it, 8a).
         Returns per row (segments int64 (N,2) | empty, segment_features (N,768) | empty, hidden).
         `tables` = (seg (R, T, 2) int32, cnt (R,) int32) device tensors: every sub-batch also leaves its fixed-stride
-        segment table there, at its rows (single-job calls only) - what segment_sharded all-gathers.
+        segment table there, at its rows (single-job calls only) - what segment_sharded all-gathers.  `after_enqueue(streams)`
+        is called once every sub-batch has been enqueued and before the results are collected: work it enqueues behind those
+        streams (the all-gather of the tables) runs while the host still waits for the last hidden states.
 
         All sub-batches of all jobs are launched first, round-robin over the streams (a sub-batch's host->device /
         device->host copies overlap the others' kernels), and collected afterwards."""
@@ -590,6 +592,8 @@ class Segmenter:
                 ev = torch.cuda.Event()
                 ev.record(st)
             pending[slot] = (st, cst, idx, hidden_h, hidden_pin, seg_pin, cnt_pin, feat, ev)
+        if after_enqueue is not None:
+            after_enqueue(streams)
         # collect in launch order: the oldest sub-batch finishes first
         n_w = len(work)
         for k in range(max(0, n_w - len(streams)), n_w):
@@ -658,10 +662,12 @@ class Segmenter:
         return self._engine.saturation_count()
 
     @torch.no_grad()
-    def call_with_tables(self, wav, pad_to=None):
+    def call_with_tables(self, wav, pad_to=None, after_enqueue=None):
         """`__call__(wav=list, in_second=False, pad_to=...)` that also returns the call's fixed-stride segment table as
         DEVICE tensors, seg (B, T, 2) int32 and cnt (B,) int32 with T = frames of the padded length: the operands of the
-        one collective of the sharded path (distributed.segment_sharded), gathered without a host round trip."""
+        one collective of the sharded path (distributed.segment_sharded), gathered without a host round trip.
+        `after_enqueue(streams, seg, cnt)` runs when all sub-batches are enqueued (the tables are complete once `streams`
+        have drained) and before the host collects the results."""
         if self.bucket_ratio:
             raise ValueError("call_with_tables pads the whole call to one length; it cannot be combined with bucket_ratio")
         rows = []
@@ -674,7 +680,8 @@ class Segmenter:
         T = eng.num_frames(max_length)
         seg = torch.empty((len(rows), T, 2), dtype=torch.int32, device=eng.device)
         cnt = torch.empty((len(rows),), dtype=torch.int32, device=eng.device)
-        results = self._run_jobs(rows, lengths, [(list(range(len(rows))), max_length)], tables=(seg, cnt))
+        hook = (lambda streams: after_enqueue(streams, seg, cnt)) if after_enqueue is not None else None
+        results = self._run_jobs(rows, lengths, [(list(range(len(rows))), max_length)], tables=(seg, cnt), after_enqueue=hook)
         outputs = [{'segments': sg, 'segment_features': feat, 'hidden_states': hid} for sg, feat, hid in results]
         return outputs, seg, cnt
 

@@ -49,6 +49,10 @@ def _worker(rank, world, port, kind, nccl, q):
         res_global = segment_sharded(seg, wav=clips, in_second=False, gather_features=True)
         lo, hi = shard_range(len(clips), rank, world)
         res_local = segment_sharded(seg, wav=clips[lo:hi], in_second=True, local_input=True)
+        # with the caller's bound on the shard size the list lengths travel inside the table block (no size collective)
+        res_hint = segment_sharded(seg, wav=clips[lo:hi], in_second=True, local_input=True, per_rank=(len(clips) + world - 1) // world)
+        assert len(res_hint) == len(res_local) and all(np.array_equal(np.asarray(a["segments"]), np.asarray(b["segments"]))
+                                                       for a, b in zip(res_hint, res_local))
         q.put((rank, [(np.asarray(r["segments"]), r["segment_features"], r["hidden_states"]) for r in res_global],
                [np.asarray(r["segments"]) for r in res_local]))
     finally:
