@@ -474,6 +474,19 @@ def run_ours(args):
             seg(wav=clips, in_second=True, pad_to=pad_to)
         torch.cuda.synchronize()
         e2e_local_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_dev_s = None
+    if world > 1:
+        # the sharded call with the hidden states left on the GPUs (hidden_to="device"): what a multi-GPU pipeline that
+        # consumes segments / features pays - the host link is shared by all ranks of the box (profiles/r03_multi_gpu.md)
+        f = lambda: segment_sharded(seg, wav=clips, in_second=True, local_input=True, pad_to=pad_to, per_rank=B, hidden_to="device")
+        for _ in range(2):
+            f()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            f()
+        torch.cuda.synchronize()
+        e2e_dev_s = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop() if rank == 0 else None
     e2e_value = frames_valid * args.steps / e2e_s
     mine = res[rank * B:(rank + 1) * B] if world > 1 else res
@@ -583,7 +596,9 @@ def run_ours(args):
                                 + ("; e2e = segment_sharded(local_input=True): forward + all-gather of counts and segment table" if world > 1 else "")},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / args.steps * 1e3,
-                **({"ms_per_step_without_the_all_gather": e2e_local_s / args.steps * 1e3} if e2e_local_s else {})},
+                **({"ms_per_step_without_the_all_gather": e2e_local_s / args.steps * 1e3} if e2e_local_s else {}),
+                **({"hidden_states_left_on_device": {"value": frames_valid * args.steps / e2e_dev_s, "ms_per_step": e2e_dev_s / args.steps * 1e3,
+                                                     "d2h_bytes_per_step": d2h - B * T * 768 * 4}} if e2e_dev_s else {})},
         "gpu_launches": eng.launch_count(True) * len(subs) * args.steps,
         "clocks": clocks,
         "roofline": roofline,

@@ -70,7 +70,7 @@ def _comm_device(segmenter, group):
 
 
 def segment_sharded(segmenter, wav_file=None, wav=None, in_second=True, group=None, local_input=False, pad_to=None,
-                    gather_features=False, per_rank=None):
+                    gather_features=False, per_rank=None, hidden_to="host"):
     """`Segmenter.__call__` for a LIST of utterances sharded over the ranks of `group` (one process per GPU).
 
     Every rank calls this collectively.  With `local_input=False` (default) every rank passes the same global list and
@@ -81,6 +81,10 @@ def segment_sharded(segmenter, wav_file=None, wav=None, in_second=True, group=No
     would use - and (2) the segment table: an all-gather of the per-utterance segment counts, then of the fixed-stride
     (utterances, max count, 2) int32 table (a few KB over NCCL / NVSwitch).
 
+    `hidden_to`: where the rank's own hidden states go - "host" (NumPy, default), "device" (torch CUDA tensors: they stay
+    sharded ON the GPUs, which is what a multi-GPU pipeline that consumes segments / features wants: the host link is
+    shared by all ranks of a box and 49 MB per 32 x 10 s per rank is what saturates it) or None.
+
     `per_rank` (with `local_input=True`): an upper bound on the number of utterances any rank passes, known to the caller
     (e.g. the per-GPU batch size).  It saves the collective that otherwise exchanges the list lengths on every call; the
     actual lengths then travel inside the segment-table block.
@@ -90,7 +94,8 @@ def segment_sharded(segmenter, wav_file=None, wav=None, in_second=True, group=No
     `segment_features` and `hidden_states` for the rank's own utterances and None for the others, unless
     `gather_features=True`, which also all-gathers the (N, 768) segment features.  Hidden states stay sharded."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        out = segmenter(wav_file=wav_file, wav=wav, in_second=in_second, pad_to=pad_to)
+        out = segmenter(wav_file=wav_file, wav=wav, in_second=in_second, pad_to=pad_to,
+                        **({"hidden_to": hidden_to} if hidden_to != "host" else {}))
         return out if isinstance(out, list) else [out]
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     items = wav_file if wav_file is not None else wav
@@ -169,7 +174,7 @@ def segment_sharded(segmenter, wav_file=None, wav=None, in_second=True, group=No
 
         _t.append(_time.perf_counter())
         if mine:
-            local, _, _ = segmenter.call_with_tables(local_kw["wav"], pad_to=pad_to, after_enqueue=exchange)
+            local, _, _ = segmenter.call_with_tables(local_kw["wav"], pad_to=pad_to, after_enqueue=exchange, hidden_to=hidden_to)
         else:
             local = []
             exchange([], None, None)
@@ -182,7 +187,7 @@ def segment_sharded(segmenter, wav_file=None, wav=None, in_second=True, group=No
         if sizes_in_block:
             sizes = [int(g[r * per_rank, 0, 1]) for r in range(world)]
     else:
-        local = segmenter(in_second=False, pad_to=pad_to, **local_kw) if mine else []
+        local = segmenter(in_second=False, pad_to=pad_to, **({"hidden_to": hidden_to} if hidden_to != "host" else {}), **local_kw) if mine else []
         # (1) counts, (2) fixed-stride table
         cnt = torch.zeros(per_rank, dtype=torch.int32)
         for k, r in enumerate(local):

@@ -514,7 +514,7 @@ class Segmenter:
         """(lo, hi) sub-batch bounds of one padded batch of n_rows rows (batching.sub_batch_bounds)."""
         return sub_batch_bounds(n_rows, self.streams, self.max_batch, self.sub_batch_sizes)
 
-    def _run_jobs(self, rows, lengths, jobs, pcm=0, tables=None, after_enqueue=None):
+    def _run_jobs(self, rows, lengths, jobs, pcm=0, tables=None, after_enqueue=None, hidden_to="host"):
         """Padded batches through the engine.  rows: 1-D fp32 CPU tensors (or int16 at `pcm` Hz when pcm != 0); jobs: list of
         (row indices, max_length) - every row of a job is padded to that job's max_length (results depend on it, 8a).
         Returns per row (segments int64 (N,2) | empty, segment_features (N,768) | empty, hidden).
@@ -522,6 +522,8 @@ class Segmenter:
         segment table there, at its rows (single-job calls only) - what segment_sharded all-gathers.  `after_enqueue(streams)`
         is called once every sub-batch has been enqueued and before the results are collected: work it enqueues behind those
         streams (the all-gather of the tables) runs while the host still waits for the last hidden states.
+        `hidden_to`: "host" (the reference contract: NumPy arrays), "device" (torch CUDA tensors, no device->host copy of the
+        hidden states - 49 MB per 32 x 10 s) or None (not returned).
 
         All sub-batches of all jobs are launched first, round-robin over the streams (a sub-batch's host->device /
         device->host copies overlap the others' kernels), and collected afterwards."""
@@ -575,12 +577,15 @@ class Segmenter:
                 # encoder first; its hidden states start their trip to the host on the slot's copy stream while the
                 # segmentation scan (latency bound, ~0.3 ms whatever the sub-batch size) and the pooling still run
                 hidden, _, _, _ = eng.forward(wav_dev, n_dev, thr_n, thr_m, segment=False, slot=slot)
-                ev_h = torch.cuda.Event()
-                ev_h.record(st)
-                cst.wait_event(ev_h)
-                with torch.cuda.stream(cst):
-                    hidden_h, hidden_pin = eng.pool.array(tuple(hidden.shape))
-                    hidden_pin.copy_(hidden, non_blocking=True)
+                if hidden_to == "host":
+                    ev_h = torch.cuda.Event()
+                    ev_h.record(st)
+                    cst.wait_event(ev_h)
+                    with torch.cuda.stream(cst):
+                        hidden_h, hidden_pin = eng.pool.array(tuple(hidden.shape))
+                        hidden_pin.copy_(hidden, non_blocking=True)
+                else:      # the forward's output buffer is reused by the slot's next forward: hand out a copy, or nothing
+                    hidden_h, hidden_pin = (hidden.clone() if hidden_to == "device" else [None] * len(idx)), None
                 seg, cnt, feat = eng.segment_states(hidden, thr_n, thr_m, slot=slot)
                 if tables is not None:
                     tables[0][idx[0]:idx[-1] + 1].copy_(seg, non_blocking=True)
@@ -605,7 +610,7 @@ class Segmenter:
         return results
 
     @torch.no_grad()
-    def __call__(self, wav_file=None, wav=None, in_second=True, pcm16=None, sample_rate=16000, pad_to=None):
+    def __call__(self, wav_file=None, wav=None, in_second=True, pcm16=None, sample_rate=16000, pad_to=None, hidden_to="host"):
         """Same contract as the reference: a dict (single input) or list of dicts with
         `segments` (N,2), `segment_features` (N,768) float32, `hidden_states` (T_max,768) float32.
 
@@ -617,7 +622,11 @@ class Segmenter:
         `pad_to=` (extension): pad the batch to at least this many 16 kHz samples instead of to its own longest clip.
         An utterance's result depends on its samples and on the padded length only (conv-0 GroupNorm runs over the
         padding), so a shard of a list padded to the WHOLE list's maximum reproduces the rows of the
-        single call bit for bit - this is what `sylber_b200.distributed.segment_sharded` passes."""
+        single call bit for bit - this is what `sylber_b200.distributed.segment_sharded` passes.
+
+        `hidden_to=` (extension): "host" (default, the reference contract: `hidden_states` is a NumPy array), "device"
+        (`hidden_states` is a torch CUDA tensor: the 1.5 MB per 10 s clip stay on the GPU for a downstream device
+        consumer) or None (`hidden_states` is None).  Segments and segment features always come back as NumPy."""
         pcm = int(sample_rate) if pcm16 is not None else 0
         if pcm:
             is_batch = isinstance(pcm16, (list, tuple))
@@ -649,7 +658,8 @@ class Segmenter:
             buckets = plan_length_buckets(lengths, self.bucket_ratio, self.max_batch)
         else:
             buckets = [list(range(len(rows)))]
-        results = self._run_jobs(rows, lengths, [(idx, max(floor, max(lengths[i] for i in idx))) for idx in buckets], pcm)
+        results = self._run_jobs(rows, lengths, [(idx, max(floor, max(lengths[i] for i in idx))) for idx in buckets], pcm,
+                                 hidden_to=hidden_to)
         outputs = [{'segments': seg * 1.0 / FRAME_RATE if in_second else seg,
                     'segment_features': feat, 'hidden_states': hid} for seg, feat, hid in results]
         return outputs if is_batch else outputs[0]
@@ -662,7 +672,7 @@ class Segmenter:
         return self._engine.saturation_count()
 
     @torch.no_grad()
-    def call_with_tables(self, wav, pad_to=None, after_enqueue=None):
+    def call_with_tables(self, wav, pad_to=None, after_enqueue=None, hidden_to="host"):
         """`__call__(wav=list, in_second=False, pad_to=...)` that also returns the call's fixed-stride segment table as
         DEVICE tensors, seg (B, T, 2) int32 and cnt (B,) int32 with T = frames of the padded length: the operands of the
         one collective of the sharded path (distributed.segment_sharded), gathered without a host round trip.
@@ -681,7 +691,8 @@ class Segmenter:
         seg = torch.empty((len(rows), T, 2), dtype=torch.int32, device=eng.device)
         cnt = torch.empty((len(rows),), dtype=torch.int32, device=eng.device)
         hook = (lambda streams: after_enqueue(streams, seg, cnt)) if after_enqueue is not None else None
-        results = self._run_jobs(rows, lengths, [(list(range(len(rows))), max_length)], tables=(seg, cnt), after_enqueue=hook)
+        results = self._run_jobs(rows, lengths, [(list(range(len(rows))), max_length)], tables=(seg, cnt), after_enqueue=hook,
+                                 hidden_to=hidden_to)
         outputs = [{'segments': sg, 'segment_features': feat, 'hidden_states': hid} for sg, feat, hid in results]
         return outputs, seg, cnt
 

@@ -198,3 +198,19 @@ def test_twelve_layer_encoder_vs_oracle():
             assert _rel(o["hidden_states"], ref[i]) < bar, (mode, i)
             _check_against_own_states(o)
         del seg
+
+
+def test_hidden_states_can_stay_on_the_device(seg9):
+    """`hidden_to="device"` / None (extension): the hidden states are not copied to the host; everything else is unchanged."""
+    gen = torch.Generator().manual_seed(8)
+    wavs = [torch.randn(1, n, generator=gen) for n in (40000, 16000, 30000)]
+    host = seg9(wav=wavs, in_second=False)
+    dev = seg9(wav=wavs, in_second=False, hidden_to="device")
+    none = seg9(wav=wavs, in_second=False, hidden_to=None)
+    for h, d, n in zip(host, dev, none):
+        assert torch.is_tensor(d["hidden_states"]) and d["hidden_states"].is_cuda
+        assert np.array_equal(d["hidden_states"].cpu().numpy(), h["hidden_states"])
+        assert n["hidden_states"] is None
+        for o in (d, n):
+            assert np.array_equal(np.asarray(o["segments"]), np.asarray(h["segments"]))
+            assert np.array_equal(np.asarray(o["segment_features"]), np.asarray(h["segment_features"]))
