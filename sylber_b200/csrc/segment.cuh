@@ -18,8 +18,10 @@
 //   * powf(|x_i|^2 + eps, .5) of every frame is computed by the parallel norm kernel;
 //   * the merged centroid (curr * cnt + x) / (cnt + 1), its squared norm and the powf of that are computed
 //     speculatively, concurrently with the cosine that decides whether the merge happens;
-//   * the 24 divisions per lane by the small integer cnt + 1 use one reciprocal and Markstein's FMA correction
-//     (div_by_count below), which is the correctly rounded quotient - bit-identical to NumPy's division.
+//   * the divisions by the small integer cnt + 1 use one reciprocal r = RN(1 / n) and Markstein's FMA correction
+//     (q0 = RN(a r), rem = a - q0 n exact in one FMA, q = RN(q0 + rem r)): with a correctly rounded reciprocal this is the
+//     correctly rounded quotient unless the significand of n is all ones (never for n <= 2^23) - bit-identical to NumPy's
+//     division (tests/test_div_by_count.py); a single guard per step falls back to IEEE division if an operand is tiny.
 #pragma once
 
 #include "common.cuh"
@@ -53,31 +55,11 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, 
                : "memory");
 }
 
-// a / n for n = float(small positive integer) with r = __frcp_rn(n): q0 = RN(a r), rem = a - q0 n (exact in one FMA),
-// q = RN(q0 + rem r).  Markstein's theorem: with a correctly rounded reciprocal this is the correctly rounded quotient
-// unless the significand of n is all ones (never for n <= 2^23) - provided nothing underflows, hence the guard.
-__device__ __forceinline__ float div_by_count(float a, float n, float r) {
-  const float q0 = __fmul_rn(a, r);
-  const float rem = __fmaf_rn(-q0, n, a);
-  const float q = __fmaf_rn(rem, r, q0);
-  return (fabsf(a) > 1e-30f) ? q : __fdiv_rn(a, n);
-}
-
 // shared-memory image of one row: the 8 pairwise blocks of 96 floats padded to 104 so that the 8 lane groups, which
 // read the same offset of different blocks, hit different banks
 constexpr int SEG_BLK_PAD = 104;
 constexpr int SEG_ROW_FLOATS = 8 * SEG_BLK_PAD;   // 832 floats = 3328 bytes
 constexpr int SEG_RING = 12;                      // rows in flight (40 KB)
-
-__device__ __forceinline__ void lane_load_smem(float (&v)[24], const float* row, int lane) {
-  const float* p = row + SEG_BLK_PAD * (lane >> 2) + 2 * (lane & 3);
-#pragma unroll
-  for (int m = 0; m < 12; ++m) {
-    const float2 t = *reinterpret_cast<const float2*>(p + 8 * m);
-    v[2 * m] = t.x;
-    v[2 * m + 1] = t.y;
-  }
-}
 
 // finish NumPy's pairwise tree from the two in-lane accumulators; result identical in all lanes
 __device__ __forceinline__ float pairwise_finish(float a0, float a1) {
@@ -323,7 +305,7 @@ segment_kernel(const float* __restrict__ states_all, const float* __restrict__ p
         for (int m = 0; m < E; ++m) {
           num[m] = __fadd_rn(__fmul_rn(curr[m], fc), x[m]);
           const float q0 = __fmul_rn(num[m], rc1);
-          cand[m] = __fmaf_rn(__fmaf_rn(-q0, fc1, num[m]), rc1, q0);     // div_by_count without its guard ...
+          cand[m] = __fmaf_rn(__fmaf_rn(-q0, fc1, num[m]), rc1, q0);     // reciprocal + FMA correction, unguarded ...
           tiny |= !(fabsf(num[m]) > 1e-30f);
         }
         if (__any_sync(0xffffffffu, tiny)) {                              // ... which is taken once for all elements

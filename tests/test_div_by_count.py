@@ -1,5 +1,5 @@
 """The segmentation scan divides the running centroid by the small integer cnt + 1 with one reciprocal and Markstein's
-FMA correction (csrc/segment.cuh div_by_count) instead of 24 IEEE divisions per lane and frame.  NumPy divides with
+FMA correction (csrc/segment.cuh, the merged-centroid update of the scan) instead of 24 IEEE divisions per lane and frame.  NumPy divides with
 the correctly rounded quotient, so the sequence must equal `a / n` bit for bit: replayed here in C with hardware FMA
 for every n <= 4096 against random numerators over 80 binades (the theorem covers all n whose significand is not all
 ones, i.e. every integer below 2^24 - 1)."""
