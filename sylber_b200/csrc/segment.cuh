@@ -195,7 +195,7 @@ segment_kernel(const float* __restrict__ states_all, const float* __restrict__ p
   __shared__ __align__(128) float ring[SEG_RING][SEG_ROW_FLOATS];
   __shared__ __align__(8) uint64_t full_bar[SEG_RING];
   __shared__ __align__(8) uint64_t empty_bar[SEG_RING];
-  __shared__ float2 part[2][2];          // [frame parity][warp]: partial sums of (curr*x) and (cand*cand)
+  __shared__ float2 part[2][2];          // [scoring-frame parity][warp]: partial sums of (curr*x) and (cand*cand)
   griddep_launch_dependents();
   const int b = blockIdx.x;
   const int lane = lane_id();
@@ -254,6 +254,8 @@ segment_kernel(const float* __restrict__ states_all, const float* __restrict__ p
     float sq_pending = 1.0f;    // (curr**2).sum() + 1e-8 of a centroid merged in the previous scoring frame
     bool pow_pending = false;
     int cnt = 0, s = -1;
+    int sc = 0;                 // scoring frames so far: the exchange buffer alternates per SCORING frame (frames in between
+                                // take no barrier), so a buffer is rewritten only after the other warp passed the next barrier
     for (int i0 = 0; i0 < T; i0 += 32) {
       const float my_pw = pw[min(i0 + lane, T - 1)];
       const int n_here = min(32, T - i0);
@@ -320,9 +322,10 @@ segment_kernel(const float* __restrict__ states_all, const float* __restrict__ p
           a0 = __fadd_rn(a0, __shfl_xor_sync(0xffffffffu, a0, o));
           b0 = __fadd_rn(b0, __shfl_xor_sync(0xffffffffu, b0, o));
         }
-        if (lane == 0) part[i & 1][w] = make_float2(a0, b0);
+        if (lane == 0) part[sc & 1][w] = make_float2(a0, b0);
         named_bar_sync(1, 64);                           // the two scan warps' partials are visible to each other
-        const float2 other = part[i & 1][w ^ 1];
+        const float2 other = part[sc & 1][w ^ 1];
+        ++sc;
         const float xy = __fadd_rn(0.0f, __fadd_rn(a0, other.x));
         const float sq_cand = __fadd_rn(__fadd_rn(0.0f, __fadd_rn(b0, other.y)), 1e-8f);
         const float sim = __fdiv_rn(__fdiv_rn(xy, p_curr), px);   // scalar path: powf denominators

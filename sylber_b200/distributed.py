@@ -78,8 +78,11 @@ def segment_sharded(segmenter, wav_file=None, wav=None, in_second=True, group=No
     own clips (global order = rank order).  The forward has no cross-utterance dependency, so the data path needs no
     collective; what is exchanged is (1) with local input and no `pad_to`, the batch-wide maximum length - an
     utterance's result depends on the padded length, so every rank pads to the T_max the single call
-    would use - and (2) the segment table: an all-gather of the per-utterance segment counts, then of the fixed-stride
-    (utterances, max count, 2) int32 table (a few KB over NCCL / NVSwitch).
+    would use - and (2) the segment table: ONE all-gather of the fixed-stride (utterances, 1 + T, 2) int32 block the forward
+    left on the device (row 0 carries the segment count; ~130 KB per rank at 32 x 10 s, over NCCL / NVSwitch), enqueued
+    behind the sub-batch streams while the host still collects the last hidden states, then one device->host copy.
+    (With `gather_features=True`, or a segmenter without device tables, counts, table and features travel as three
+    host-packed all-gathers instead.)
 
     `hidden_to`: where the rank's own hidden states go - "host" (NumPy, default), "device" (torch CUDA tensors: they stay
     sharded ON the GPUs, which is what a multi-GPU pipeline that consumes segments / features wants: the host link is
@@ -153,7 +156,9 @@ def segment_sharded(segmenter, wav_file=None, wav=None, in_second=True, group=No
         def exchange(streams, seg_dev, cnt_dev):
             # enqueued behind the sub-batch streams while the host still waits for the last hidden states: fill the block,
             # ONE all-gather, one copy of the gathered table into pinned memory
+            issuing = torch.cuda.current_stream(gdev)
             with torch.cuda.stream(comm):
+                comm.wait_stream(issuing)                 # `block` was zeroed on the caller's stream
                 for st in streams:
                     comm.wait_stream(st)
                 if seg_dev is not None:
