@@ -201,6 +201,19 @@ __global__ void valid_frames_kernel(const int32_t* __restrict__ n_samples, int b
   }
 }
 
+// trimmed mode: order[k] = index of the utterance with the k-th largest valid length (ties by index); one block, B <= 1024
+__global__ void length_order_kernel(const int32_t* __restrict__ valid, int batch, int32_t* __restrict__ order) {
+  for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+    const int v = valid[b];
+    int rank = 0;
+    for (int o = 0; o < batch; ++o) {
+      const int vo = valid[o];
+      rank += (vo > v) || (vo == v && o < b);
+    }
+    order[rank] = b;
+  }
+}
+
 __global__ void fill_i32_kernel(int32_t* p, int n, int v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -309,6 +322,7 @@ struct Plan {
   uint64_t last_use = 0;   // LRU stamp
   int uses = 0;            // forwards run with this plan: a CUDA graph is only captured from the second one on
   int batch = 0, t_samp = 0;
+  bool order_valid = false;   // trimmed mode: the length-order array of this plan's workspace has been written by a forward
   void* ws = nullptr;
   float* hidden = nullptr;
   WsLayout lay;
@@ -531,7 +545,7 @@ WsLayout make_layout(int batch, int t_samp) {
   w.mom = take(B * (size_t)((w.L[0] + MOM_T_PER_BLOCK - 1) / MOM_T_PER_BLOCK) * C0_NMOM * sizeof(double));
   w.gn_scale = take(B * kC * sizeof(float));
   w.gn_shift = take(B * kC * sizeof(float));
-  w.valid = take(8 * B * sizeof(int32_t));   // frames, then needed rows of conv0..conv6 (valid_frames_kernel)
+  w.valid = take(9 * B * sizeof(int32_t));   // frames, needed rows of conv0..conv6 (valid_frames_kernel), length order
   w.nsq = take(2 * M * sizeof(float));   // squared norms, then their scalar powf (segment.cuh)
   w.seg_scratch = take(B * 6 * (size_t)(w.T + 1) * sizeof(int32_t));
   for (int i = 0; i < 6; ++i) {
@@ -698,6 +712,7 @@ int build_plan(syl_handle* h, int batch, int t_samp, void* ws, float* hidden) {
   h->plan_cur = victim;
   Plan& pl = h->plans[h->plan_cur];
   pl.valid = false;
+  pl.order_valid = false;
   pl.uses = 0;
   pl.last_use = ++h->plan_clock;
   for (auto& g : pl.graphs) cudaGraphExecDestroy(g.exec);
@@ -851,7 +866,7 @@ long long* g_attn_trace = nullptr;   // set by syl_attention_trace for one launc
 int g_attn_trace_cap = 0;
 
 int launch_attention(const CUtensorMap& qkv, const CUtensorMap& o_hi, const CUtensorMap& o_lo, const int32_t* kv_len,
-                     int B, int T, int out_lo, int sm_count, cudaStream_t st, int trim = 0) {
+                     int B, int T, int out_lo, int sm_count, cudaStream_t st, int trim = 0, const int32_t* order = nullptr) {
   AttnParams ap;
   ap.trace = g_attn_trace;
   ap.trace_cap = g_attn_trace_cap;
@@ -862,6 +877,7 @@ int launch_attention(const CUtensorMap& qkv, const CUtensorMap& o_hi, const CUte
   ap.kv_len = kv_len;
   ap.out_lo = out_lo;
   ap.trim = trim && kv_len != nullptr;
+  ap.order = order;
   // experiment switches (profiles/r02_attention.md): SYL_ATTN_POLY = exp2 pairs (out of every four) computed on the
   // FMA pipe (0 or 1), SYL_ATTN_DEBUG = arithmetic-removal probes
 #ifdef SYL_DIAG
@@ -936,7 +952,8 @@ int run_layer(syl_handle* h, int l, float* h_out, cudaStream_t st) {
   }
   {
     StageTimer tm(h, ST_ATTN, st);
-    if (launch_attention(pl.attn_map, pl.ctx_hi_map, pl.ctx_lo_map, at<int32_t>(ws, L.valid), B, T, split_enc, h->sm_count, st, h->trim))
+    if (launch_attention(pl.attn_map, pl.ctx_hi_map, pl.ctx_lo_map, at<int32_t>(ws, L.valid), B, T, split_enc, h->sm_count, st, h->trim,
+                         h->trim && pl.order_valid ? at<int32_t>(ws, L.valid) + 8 * B : nullptr))
       return fail(h, SYL_E_CUDA, "attention launch failed: %s", launch_err());
   }
   {
@@ -1155,7 +1172,7 @@ int syl_forward_launch_count(const syl_handle* h, int with_segmentation) {
   if (!h) return 0;
   const int nl = (h->active_layers >= 0 && h->active_layers < h->n_layers) ? h->active_layers : h->n_layers;
   // valid_frames, moments, gn_coeff, conv0_mma, 6 conv GEMMs, LN512, proj, pos, LN ; per layer 4 GEMM + attn + 2 LN
-  return 4 + 6 + 4 + nl * 7 + (with_segmentation ? 3 : 0);
+  return 4 + 6 + 4 + nl * 7 + (with_segmentation ? 3 : 0) + (h->trim ? 1 : 0);   // + length_order_kernel in trimmed mode
 }
 
 // enqueue every kernel of one forward on `st` (eagerly, or into a stream capture)
@@ -1169,6 +1186,9 @@ static int enqueue_forward(syl_handle* h, Plan& pl, const float* wav, const int3
   const bool split_proj = h->mode & SYL_SPLIT_FPROJ, split_enc = h->mode & SYL_SPLIT_ENC;
   int rc;
   valid_frames_kernel<<<(batch + 127) / 128, 128, 0, st>>>(n_samples, batch, T, at<int32_t>(workspace, L.valid));
+  pl.order_valid = h->trim;
+  if (h->trim)
+    length_order_kernel<<<1, 128, 0, st>>>(at<int32_t>(workspace, L.valid), batch, at<int32_t>(workspace, L.valid) + 8 * batch);
   if ((rc = run_frontend(h, wav, st))) return rc;
   {
     StageTimer tm(h, ST_LN, st);

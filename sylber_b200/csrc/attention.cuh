@@ -44,6 +44,8 @@ struct AttnParams {
   const int* kv_len;      // [B] number of valid keys per utterance (== T when nothing is padded), or null
   int out_lo;             // also write the fp16 lo part through map o_lo
   int trim;               // trimmed mode: query tiles at or beyond kv_len[b] (padded frames) are not computed
+  const int* order;       // trimmed mode: utterance indices sorted by valid length, longest first (null = identity), so that
+                          // the statically strided items of one round cost about the same on every CTA
   int debug;              // timing experiments only (SYL_ATTN_DEBUG): 2 skip exp, 4 skip P store
   long long* trace;       // timeline probe (tools/attn_trace.py): CTA 0 logs clock64 stamps, 7 writers x trace_cap
   int trace_cap;
@@ -250,6 +252,7 @@ attention7_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_cons
     const int bh = item / n_groups;
     h = bh % p.heads;
     b = bh / p.heads;
+    if (p.order != nullptr) b = __ldg(p.order + b);
     q0 = grp * ATT_QT * ATT_BQ;
     const int tiles_b = p.trim ? (item_kv_len(b) + ATT_BQ - 1) / ATT_BQ : q_tiles;
     n_act = min(ATT_QT, tiles_b - grp * ATT_QT);
