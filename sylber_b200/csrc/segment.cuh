@@ -10,9 +10,16 @@
 //   * row means are sequential row-by-row accumulations followed by a division.
 //   * `np.float32 ** .5` on a NumPy *scalar* is libm powf(x, .5f), not sqrtf: powf_half() below replays
 //     glibc's powf (FMA build, as selected on every AVX2 x86-64 host) in fp64, see powf_tables.cuh.
-// The scan over frames is inherently serial per utterance (each decision depends on the running centroid);
-// parallelism comes from one warp per utterance plus the 32 lanes over the 768 features.  What bounds the scan is
-// therefore the LATENCY of one frame step, and the kernel is organised around that (round 3):
+// The scan over frames is serial inside a RUN (a maximal stretch of frames above the norm threshold: each decision
+// depends on the running centroid), but runs are independent of each other: a masked-off frame resets the scan state
+// (segment_utils.py:83-89), a mid-boundary only ever joins two segments of one run, and the refinement window stays
+// inside those two segments (:110-128).  So the work item is a run, not an utterance: CTA (c, b) owns the runs of
+// utterance b that START in frames [32 c, 32 c + 32) and follows the last of them to its end; the segments of a CTA go
+// to slots (first run start + k) of a frame-indexed table, which cannot collide with another CTA's because a segment has
+// at least one frame; the last CTA of an utterance to finish compacts the table in frame order (segment_utils.py:130).
+// One run spanning the whole utterance costs what the one-CTA-per-utterance kernel did; speech (pauses) and the synthetic
+// bench states (15 % of the frames below the threshold) split into many.  Inside a run what bounds the scan is
+// the LATENCY of one frame step, and the kernel is organised around that (round 3):
 //   * the rows of the utterance stream into a shared-memory ring by bulk async copies (cp.async.bulk + mbarrier)
 //     issued SEG_RING frames ahead, so no step waits on an L2 / HBM round trip;
 //   * powf(|x_i|^2 + eps, .5) of every frame is computed by the parallel norm kernel;
@@ -133,8 +140,13 @@ __device__ __forceinline__ float np_sum_serial(const float* a, int n) { return _
 // pw[i] = +-powf(nsq[i], .5f) - the denominator the scalar cossim of the scan uses for frame i (segment_utils.py:96),
 // with the sign carrying the norm-threshold decision of segment_utils.py:76 (array path: sqrt): negative = masked off
 // ----------------------------------------------------------------------------------------------
+// It also resets what segment_kernel's CTAs share per utterance (scratch layout below): the end of slot i of the segment
+// table to SEG_SLOT_UNUSED and, from frame 0, the count of finished CTAs.
+constexpr int32_t SEG_SLOT_UNUSED = (int32_t)0x80000000;
+
 __global__ void __launch_bounds__(256)
-frame_sqnorm_kernel(const float* __restrict__ states, int rows, float thr_norm, float* __restrict__ nsq, float* __restrict__ pw) {
+frame_sqnorm_kernel(const float* __restrict__ states, int rows, int T, float thr_norm, float* __restrict__ nsq, float* __restrict__ pw,
+                    int32_t* __restrict__ scratch_all) {
   griddep_launch_dependents();
   griddep_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -148,6 +160,10 @@ frame_sqnorm_kernel(const float* __restrict__ states, int rows, float thr_norm, 
     nsq[row] = v;
     const float p = powf_half(v);        // > 0 for every finite v >= 1e-8; NaN stays NaN and compares "off" like NumPy's >=
     pw[row] = (__fsqrt_rn(v) >= thr_norm) ? p : -p;
+    const int b = row / T, i = row - b * T;
+    int32_t* scratch = scratch_all + (size_t)b * 6 * (T + 1);
+    scratch[(T + 1) + i] = SEG_SLOT_UNUSED;      // seg_e[i]
+    if (i == 0) scratch[T] = 0;                  // CTAs of this utterance that have finished (segment_kernel)
   }
 }
 
@@ -182,12 +198,18 @@ __device__ __forceinline__ void lane_mean_rows(LaneVec& acc, const float* __rest
 }
 
 // ----------------------------------------------------------------------------------------------
-// segmentation: one warp per utterance.
-//   states  [B, T, 768] fp32           nsq [B, T]  from frame_sqnorm_kernel
+// segmentation: grid (ceil(T / 32), B) - CTA (c, b) owns the runs of utterance b that start in frames [32 c, 32 c + 32).
+//   states  [B, T, 768] fp32           pw [B, T]  from frame_sqnorm_kernel (sign = norm-threshold decision)
 //   seg     [B, max_seg, 2] int32 out  seg_count [B] out
-//   scratch [B, 6*(T+1)] int32/float workspace (segment starts/ends/dead flags, boundaries, sweep sims)
+//   scratch [B, 6*(T+1)] int32/float workspace, six arrays of T + 1 per utterance:
+//     seg_s, seg_e   slot table: a CTA whose first run starts at frame f0 keeps its k-th segment in slot f0 + k (its
+//                    segments start at distinct frames >= f0, so slot f0 + k lies before the first frame of any later
+//                    CTA's runs); seg_e < 0 = absorbed (-1 - end) or SEG_SLOT_UNUSED; seg_s[T] counts finished CTAs
+//     mid_bd, mid_seg  the CTA's mid-boundaries, slots f0 + k likewise
+//     sim_prev, sim_next  sweep cosines, indexed by frame (the window lies inside the CTA's own runs)
 // ----------------------------------------------------------------------------------------------
 constexpr int SEG_SCAN_THREADS = 96;     // warps 0, 1: the scan; warp 2: one thread that keeps the row ring full
+constexpr int SEG_CHUNK = 32;            // run starts per CTA: one ballot
 
 __global__ void __launch_bounds__(SEG_SCAN_THREADS)
 segment_kernel(const float* __restrict__ states_all, const float* __restrict__ pw_all, int T, float thr_merge,
@@ -197,18 +219,13 @@ segment_kernel(const float* __restrict__ states_all, const float* __restrict__ p
   __shared__ __align__(8) uint64_t empty_bar[SEG_RING];
   __shared__ float2 part[2][2];          // [scoring-frame parity][warp]: partial sums of (curr*x) and (cand*cand)
   griddep_launch_dependents();
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;
+  const int c0 = blockIdx.x * SEG_CHUNK;
   const int lane = lane_id();
   const int w = threadIdx.x >> 5;
   const float* states = states_all + (size_t)b * T * SEG_D;
   const float* pw = pw_all + (size_t)b * T;
   int32_t* scratch = scratch_all + (size_t)b * 6 * (T + 1);
-  int32_t* seg_s = scratch;
-  int32_t* seg_e = scratch + (T + 1);
-  int32_t* mid_bd = scratch + 2 * (T + 1);
-  int32_t* mid_seg = scratch + 3 * (T + 1);
-  float* sim_prev = reinterpret_cast<float*>(scratch + 4 * (T + 1));
-  float* sim_next = reinterpret_cast<float*>(scratch + 5 * (T + 1));
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int k = 0; k < SEG_RING; ++k) {
@@ -220,15 +237,43 @@ segment_kernel(const float* __restrict__ states_all, const float* __restrict__ p
   __syncthreads();
   griddep_wait();
 
+  // ---- the frames this CTA scans: [f0, f1) = from the first run start inside its chunk to the end of the run that
+  // starts last inside it (every warp evaluates this redundantly; a chunk without a run start has f0 = f1)
+  int f0 = 0, f1 = 0;
+  {
+    const int i = c0 + lane;
+    const bool start = i < T && pw[i] > 0.0f && !(i > 0 && pw[i - 1] > 0.0f);
+    const unsigned m = __ballot_sync(0xffffffffu, start);
+    if (m != 0u) {
+      f0 = c0 + __ffs(m) - 1;
+      f1 = T;
+      for (int j0 = c0 + 32 - __clz(m); j0 < T; j0 += 32) {      // first masked-off frame behind the last run start
+        const int idx = j0 + lane;
+        const unsigned off = __ballot_sync(0xffffffffu, idx < T && !(pw[idx] > 0.0f));
+        if (off != 0u) {
+          f1 = j0 + __ffs(off) - 1;
+          break;
+        }
+      }
+    }
+  }
+  const int nfr = f1 - f0;
+  int32_t* seg_s = scratch + f0;
+  int32_t* seg_e = scratch + (T + 1) + f0;
+  int32_t* mid_bd = scratch + 2 * (T + 1) + f0;
+  int32_t* mid_seg = scratch + 3 * (T + 1) + f0;
+  float* sim_prev_all = reinterpret_cast<float*>(scratch + 4 * (T + 1));
+  float* sim_next_all = reinterpret_cast<float*>(scratch + 5 * (T + 1));
+
   if (w == 2) {
-    // ---- producer: row r of the utterance -> ring slot r % SEG_RING as eight 384-byte bulk copies (one per pairwise
+    // ---- producer: frame f0 + r -> ring slot r % SEG_RING as eight 384-byte bulk copies (one per pairwise
     // block, into the padded image), re-armed as soon as both scan warps have released the slot
     if (lane == 0) {
-      for (int r = 0; r < T; ++r) {
+      for (int r = 0; r < nfr; ++r) {
         const int slot = r % SEG_RING;
         if (r >= SEG_RING) mbar_wait(&empty_bar[slot], (uint32_t)(r / SEG_RING - 1) & 1u);
         mbar_arrive_expect_tx(&full_bar[slot], SEG_D * sizeof(float));
-        const float* src = states + (size_t)r * SEG_D;
+        const float* src = states + (size_t)(f0 + r) * SEG_D;
 #pragma unroll
         for (int k = 0; k < 8; ++k) bulk_copy_g2s(&ring[slot][SEG_BLK_PAD * k], src + 96 * k, 96 * sizeof(float), &full_bar[slot]);
       }
@@ -256,16 +301,17 @@ segment_kernel(const float* __restrict__ states_all, const float* __restrict__ p
     int cnt = 0, s = -1;
     int sc = 0;                 // scoring frames so far: the exchange buffer alternates per SCORING frame (frames in between
                                 // take no barrier), so a buffer is rewritten only after the other warp passed the next barrier
-    for (int i0 = 0; i0 < T; i0 += 32) {
-      const float my_pw = pw[min(i0 + lane, T - 1)];
-      const int n_here = min(32, T - i0);
+    for (int r0 = 0; r0 < nfr; r0 += 32) {
+      const float my_pw = pw[min(f0 + r0 + lane, T - 1)];
+      const int n_here = min(32, nfr - r0);
       for (int j = 0; j < n_here; ++j) {
-        const int i = i0 + j;
+        const int r = r0 + j;
+        const int i = f0 + r;
         const float pxs = __shfl_sync(0xffffffffu, my_pw, j);
         const bool on = pxs > 0.0f;
         const float px = fabsf(pxs);
-        const int slot = i % SEG_RING;
-        mbar_wait(&full_bar[slot], (uint32_t)(i / SEG_RING) & 1u);
+        const int slot = r % SEG_RING;
+        mbar_wait(&full_bar[slot], (uint32_t)(r / SEG_RING) & 1u);
         float x[E];
         if (on) {
           const float* row = &ring[slot][ring_off];
@@ -344,8 +390,8 @@ segment_kernel(const float* __restrict__ states_all, const float* __restrict__ p
         }
       }
     }
-    if (s > -1) {
-      if (threadIdx.x == 0) { seg_s[nseg] = s; seg_e[nseg] = T; }
+    if (s > -1) {                                        // closed by the masked-off frame f1, or by the end of the utterance
+      if (threadIdx.x == 0) { seg_s[nseg] = s; seg_e[nseg] = f1; }
       ++nseg;
     }
   }
@@ -378,6 +424,8 @@ segment_kernel(const float* __restrict__ states_all, const float* __restrict__ p
     const int lo = max(as, bd - max(1, la / 2));
     const int hi = min(be, bd + max(1, lb / 2));
     const int W = hi - lo;
+    float* sim_prev = sim_prev_all + lo;
+    float* sim_next = sim_next_all + lo;
     const float na = __fsqrt_rn(aa), nb = __fsqrt_rn(bb);   // 2-D path of cossim: sqrt
     for (int r = 0; r < W; ++r) {
       LaneVec x;
@@ -414,15 +462,43 @@ segment_kernel(const float* __restrict__ states_all, const float* __restrict__ p
   }
 
   // ---- phase 3: drop absorbed segments (segment_utils.py:130-131) ----
+  // This CTA's slots are final.  The last CTA of the utterance to get here packs the slot table in frame order
+  // (fence + counter: the pattern of the threadFenceReduction sample; the counter was zeroed by frame_sqnorm_kernel).
+  __syncwarp();
+  int last = 0;
   if (lane == 0) {
-    int n = 0;
+    __threadfence();
+    last = atomicAdd(scratch + T, 1) == (int)gridDim.x - 1;
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+  __threadfence();
+  {
+    const int32_t* all_s = scratch;
+    const int32_t* all_e = scratch + (T + 1);
     int32_t* out = seg_all + (size_t)b * max_seg * 2;
-    for (int i = 0; i < nseg; ++i) {
-      if (seg_e[i] < 0) continue;
-      if (n < max_seg) { out[2 * n] = seg_s[i]; out[2 * n + 1] = seg_e[i]; }
-      ++n;
+    int n = 0;
+    for (int i0 = 0; i0 < T; i0 += 128) {
+      int32_t e[4], st[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {      // four independent pairs of loads in flight
+        const int i = i0 + 32 * u + lane;
+        e[u] = i < T ? __ldcg(all_e + i) : SEG_SLOT_UNUSED;
+        st[u] = i < T ? __ldcg(all_s + i) : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool alive = e[u] >= 0;
+        const unsigned m = __ballot_sync(0xffffffffu, alive);
+        const int pos = n + __popc(m & ((1u << lane) - 1u));
+        if (alive && pos < max_seg) {
+          out[2 * pos] = st[u];
+          out[2 * pos + 1] = e[u];
+        }
+        n += __popc(m);
+      }
     }
-    seg_count[b] = n;
+    if (lane == 0) seg_count[b] = n;
   }
 }
 

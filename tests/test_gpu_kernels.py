@@ -117,6 +117,62 @@ def test_segmentation_edge_cases(lib, cuda):
     assert cnt[0] == 0 and cnt[1] == 1 and cnt[2] >= 20
 
 
+def _speechy(rng, T, on_mask):
+    """plateau states whose frames are forced above / below the norm threshold by `on_mask`"""
+    st = plateau_states(rng, T, sil=0.0)
+    nrm = np.linalg.norm(st, axis=1, keepdims=True)
+    st = st / nrm * rng.uniform(2.7, 3.6, (T, 1)).astype(np.float32)
+    st[~on_mask] *= np.float32(0.01)
+    return st.astype(np.float32)
+
+
+def test_segmentation_run_structure(lib, cuda):
+    """The scan is parallel over runs (stretches of frames above the norm threshold), one CTA per 32-frame chunk of run
+    starts (segment.cuh): runs that start / end exactly on chunk borders, one run through every chunk, runs longer than a
+    chunk behind short ones, T a multiple of 32 and not, a run reaching the last frame."""
+    rng = np.random.default_rng(21)
+    cases = []
+    for T in (32, 33, 64, 499, 1000):
+        on = np.ones(T, bool)
+        cases.append((T, on.copy()))                       # one run: every CTA but the first has nothing to do
+        on = np.ones(T, bool); on[31::32] = False           # every run ends on the last frame of a chunk
+        cases.append((T, on.copy()))
+        on = np.ones(T, bool); on[0::32] = False            # every run starts on frame 1 of a chunk
+        cases.append((T, on.copy()))
+        on = np.ones(T, bool); on[32::32] = False; on[0] = False
+        cases.append((T, on.copy()))
+        on = rng.random(T) < 0.85                           # the bench's occupancy: short runs
+        cases.append((T, on.copy()))
+        on = np.zeros(T, bool); on[T // 3:] = True          # silence, then one run to the end
+        cases.append((T, on.copy()))
+        on = np.ones(T, bool); on[5] = False; on[7] = False; on[T - 1] = False   # short runs, then a long one from chunk 0
+        cases.append((T, on.copy()))
+    for T, on in cases:
+        st = _speechy(rng, T, on)[None]
+        _check_segmentation(lib, cuda, st)
+
+
+def test_segmentation_reuses_workspace(lib, cuda):
+    """The slot table and the finished-CTA counter live in the caller's workspace and are reset by every call: two
+    different batches through ONE workspace, each equal to the oracle (a stale slot would add a segment)."""
+    rng = np.random.default_rng(22)
+    B, T = 4, 300
+    need = lib.syl_segment_workspace_bytes(B, T)
+    ws = torch.full((need,), 0x5a, dtype=torch.uint8, device=cuda)          # garbage, not zeros
+    seg = torch.zeros((B, T, 2), dtype=torch.int32, device=cuda)
+    cnt = torch.zeros((B,), dtype=torch.int32, device=cuda)
+    for rep in range(3):
+        st = np.stack([plateau_states(rng, T, sil=[0.25, 0.0, 0.6][rep]) for _ in range(B)])
+        sd = torch.from_numpy(st).to(cuda)
+        rc = lib.syl_segment(G.ptr(sd), B, T, float(np.float32(2.6)), float(np.float32(0.8)), G.ptr(seg), G.ptr(cnt), G.ptr(None), T,
+                             G.ptr(ws), need, G.stream())
+        assert rc == 0
+        torch.cuda.synchronize()
+        for b in range(B):
+            want = R.c_get_segment(st[b], 2.6, 0.8)
+            assert np.array_equal(seg[b, :int(cnt[b])].cpu().numpy().astype(np.int64), want), (rep, b)
+
+
 def test_segmentation_golden(lib, cuda):
     import os
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "segment_cases.npz"))

@@ -117,3 +117,48 @@ def test_against_live_reference():
         want = ref.get_segment(st, 2.6, 0.8)
         assert _same_segments(R.get_segment(st, 2.6, 0.8), want)
         assert _same_segments(R.c_get_segment(st, 2.6, 0.8), want)
+
+
+# ------------------------------------------------------------------------------------------------
+# The CUDA scan is parallel over RUNS (csrc/segment.cuh): CTA c owns the runs that start in frames [32 c, 32 c + 32),
+# keeps its k-th segment in slot (first run start + k) of a frame-indexed table, and the table is packed in frame
+# order.  This CPU model of that decomposition (the oracle applied to each CTA's frame range) must equal the oracle
+# on the whole utterance: it is the property the kernel's structure rests on (segment_utils.py:83-89: a masked-off
+# frame resets the scan; :110-128: a mid-boundary only touches the two segments of one run).
+# ------------------------------------------------------------------------------------------------
+def _cta_ranges(on, chunk):
+    T = len(on)
+    for c0 in range(0, T, chunk):
+        starts = [i for i in range(c0, min(T, c0 + chunk)) if on[i] and (i == 0 or not on[i - 1])]
+        if not starts:
+            continue
+        end = starts[-1] + 1
+        while end < T and on[end]:
+            end += 1
+        yield starts[0], end
+
+
+def _run_parallel_model(states, norm_thr, merge_thr, chunk):
+    T = len(states)
+    on = ((states ** 2).sum(-1) + 1e-8) ** .5 >= norm_thr
+    slot_s = np.zeros(T, np.int64)
+    slot_e = np.full(T, -1, np.int64)             # < 0: unused (the kernel's SEG_SLOT_UNUSED / absorbed marker)
+    for f0, f1 in _cta_ranges(on, chunk):
+        runs, splits = R._scan(states[f0:f1], on[f0:f1], merge_thr)
+        assert f0 + len(runs) <= f1               # phase-1 slots stay inside the CTA's own frames
+        for k, (s, e) in enumerate(R._refine(states[f0:f1], runs, splits, merge_thr)):
+            assert slot_e[f0 + k] < 0
+            slot_s[f0 + k], slot_e[f0 + k] = s + f0, e + f0
+    keep = slot_e >= 0
+    return np.stack([slot_s[keep], slot_e[keep]], 1)
+
+
+@pytest.mark.parametrize("chunk", [4, 32])
+def test_runs_are_independent(chunk):
+    rng = np.random.default_rng(5)
+    for _ in range(60):
+        T = int(rng.integers(1, 300))
+        st = plateau_states(rng, T, noise=float(rng.uniform(0.1, 0.6)), sil=float(rng.uniform(0.0, 0.5)))
+        want = np.asarray(R.get_segment(st, 2.6, 0.8)).reshape(-1, 2)
+        got = _run_parallel_model(st, 2.6, 0.8, chunk)
+        assert want.shape == got.shape and np.array_equal(want, got)
