@@ -156,6 +156,9 @@ int syl_gemm_f32(const float* A, const float* W, const float* bias, const float*
 /* diagnostic build only: cycles for `iters` x 4 back-to-back tcgen05.mma (M=128, N=n, K=16) issued by one thread of each of
  * `ctas` CTAs; writes the elapsed clock64 ticks of CTA 0 to cycles_out_dev (one int64) */
 int syl_mma_probe(int n, int iters, int ctas, void* cycles_out_dev, void* stream);
+/* diagnostic build only: every following GEMM launch writes the clock64 timeline of its CTA 0 to trace_dev (128 int64;
+ * slots in csrc/gemm_tc.cuh); null switches the probe off */
+int syl_gemm_set_trace(void* trace_dev);
 #endif
 /* y[i] = powf(x[i], 0.5f) as glibc computes it (the fp64 replay used by the segmentation kernel) */
 int syl_powf_half(const float* x, float* y, int64_t n, void* stream);

@@ -66,6 +66,7 @@ SIGNATURES = {
 DIAG_SIGNATURES = {
     "syl_attention_trace": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_int, _c_void_p]),
     "syl_mma_probe": (_c_int, [_c_int, _c_int, _c_int, _c_void_p, _c_void_p]),
+    "syl_gemm_set_trace": (_c_int, [_c_void_p]),
 }
 _SO_DIAG = os.path.join(_PKG, "libsylber_b200_diag.so")
 
@@ -82,11 +83,12 @@ def _sources():
         os.path.join(os.path.dirname(_PKG), "include", "sylber_b200.h")]
 
 
-def build_library(force: bool = False, verbose: bool = False, diag: bool = False) -> str:
+def build_library(force: bool = False, verbose: bool = False, diag: bool = False, defines=(), out: str = None) -> str:
     """Compile csrc/api.cu for sm_100a into sylber_b200/libsylber_b200.so (in-tree so it travels to the GPU box).
     `diag=True` builds libsylber_b200_diag.so with -DSYL_DIAG instead: the SYL_* environment switches and the
-    diagnostic entry points (DIAG_SIGNATURES), which the product library does not contain."""
-    _SO = _SO_DIAG if diag else globals()["_SO"]
+    diagnostic entry points (DIAG_SIGNATURES), which the product library does not contain.  `defines` / `out` build a
+    variant for an A/B measurement into another file (tools/ab_lib.sh swaps it in on the GPU box)."""
+    _SO = out or (_SO_DIAG if diag else globals()["_SO"])
     if not force and os.path.exists(_SO):
         newest = max(os.path.getmtime(s) for s in _sources())
         if os.path.getmtime(_SO) >= newest:
@@ -100,6 +102,8 @@ def build_library(force: bool = False, verbose: bool = False, diag: bool = False
            "-o", tmp, os.path.join(_CSRC, "api.cu")]
     if diag:
         cmd.insert(1, "-DSYL_DIAG")
+    for d in defines:
+        cmd.insert(1, "-D" + d)
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     try:

@@ -616,8 +616,17 @@ bool make_o_maps(syl_handle* h, GemmOp& op, float* f32, __half* hi, __half* lo, 
   return true;
 }
 
+#ifdef SYL_DIAG
+long long* g_gemm_trace = nullptr;       // syl_gemm_set_trace: timeline probe of the next GEMM launches (tools/gemm_trace.py)
+#endif
+
 int launch_gemm3_raw(const GemmOp& op, const CUtensorMap& b_hi, const CUtensorMap& b_lo, cudaStream_t st, int sm_count) {
+#ifdef SYL_DIAG
+  GemmParams p = op.p;
+  p.trace = g_gemm_trace;
+#else
   const GemmParams& p = op.p;
+#endif
   const int tiles_m = p.batches * ((p.rows_per_batch + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M));
   const int tiles = tiles_m * (p.N / GEMM_BLOCK_N);
   const int clusters = std::min(tiles, sm_count / 2);
@@ -1523,6 +1532,11 @@ int syl_gemm_f32(const float* A, const float* W, const float* bias, const float*
 }
 
 #ifdef SYL_DIAG
+int syl_gemm_set_trace(void* trace_dev) {
+  g_gemm_trace = reinterpret_cast<long long*>(trace_dev);
+  return SYL_OK;
+}
+
 int syl_mma_probe(int n, int iters, int ctas, void* cycles_out_dev, void* stream) {
   SYL_ENTER();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -29,6 +29,10 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
                const __grid_constant__ CUtensorMap o_f32, const __grid_constant__ CUtensorMap o_hi,
                const __grid_constant__ CUtensorMap o_lo, const GemmParams p) {
   griddep_launch_dependents();
+  if (threadIdx.x == 0) {
+    GEMM_TRACE_NS(p, 0);
+    GEMM_TRACE(p, 1);
+  }
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // SWIZZLE_128B tiles need 1024-byte aligned stage buffers
@@ -79,6 +83,7 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
   cluster_sync_all();                        // barriers of both CTAs are initialised before anyone touches them
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
+  if (threadIdx.x == 0) GEMM_TRACE(p, 2);
   griddep_wait();                            // the predecessor kernel's output (our A operand, valid_rows) is complete
   // Trimmed mode (p.skip_invalid_tiles): M tiles that start in an utterance's padding are not computed.  The tile list
   // every role walks is COMPACTED - cluster c takes the c-th, (c + C)-th, ... computed tile - so the persistent grid
@@ -137,6 +142,7 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
                           kk * GEMM_BLOCK_K, row0, batch);
           tma_load_2d_2sm(smem_b + stage * GEMM2_B_BYTES, b_is_lo ? &b_lo : &b_hi, full_leader,
                           kk * GEMM_BLOCK_K, n_tile * GEMM_BLOCK_N + (int)cta_rank * 128);
+          if (tile == cluster_id && kb == 0) GEMM_TRACE(p, 3);
           if (++stage == GEMM2_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -156,10 +162,12 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after_sync();
+        GEMM_TRACE(p, 8 + 3 * ((tile - cluster_id) / num_clusters));
         const uint32_t tmem_d = tmem_base + acc * GEMM_BLOCK_N;
         for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
+          if (kb == 0) GEMM_TRACE(p, 9 + 3 * ((tile - cluster_id) / num_clusters));
           const uint64_t adesc = make_desc_k_sw128(smem_u32(smem_a + stage * GEMM2_A_BYTES));
           const uint64_t bdesc = make_desc_k_sw128(smem_u32(smem_b + stage * GEMM2_B_BYTES));
 #pragma unroll
@@ -174,6 +182,7 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
           }
         }
         umma_commit_2cta(&tmem_full[acc]);  // accumulator complete -> epilogue warps of both CTAs
+        GEMM_TRACE(p, 10 + 3 * ((tile - cluster_id) / num_clusters));
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -221,6 +230,7 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
+      if (ew == 0 && lane == 0) GEMM_TRACE(p, 64 + 2 * it);
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * GEMM_BLOCK_N + cb * 64);
       uint32_t r[2][16];
       tmem_ld_32x32b_x16(taddr0, r[0]);
@@ -310,6 +320,7 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
       }
       tc_fence_before_sync();
       __syncwarp();
+      if (ew == 0 && lane == 0) GEMM_TRACE(p, 65 + 2 * it);
       if (lane == 0) mbar_arrive_remote(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
       if (++acc == 2) {
         acc = 0;
@@ -318,6 +329,7 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
       ++it;                                   // bias staging parity: counts processed tiles only
     }
     if (lane == 0) tma_store_wait_all();   // bulk stores must be complete before the CTA exits
+    if (ew == 0 && lane == 0) GEMM_TRACE(p, 100);
   }
 
   tc_fence_before_sync();
@@ -325,6 +337,10 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
   if (warp == 2) {
     tc_fence_after_sync();
     tmem_dealloc_2cta<GEMM_TMEM_COLS>(tmem_base);
+  }
+  if (threadIdx.x == 0) {
+    GEMM_TRACE(p, 101);
+    GEMM_TRACE_NS(p, 102);
   }
 }
 

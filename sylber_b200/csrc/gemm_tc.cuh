@@ -38,6 +38,31 @@ struct GemmParams {
   int act;                  // 0 none, 1 GELU
   float col_scale;          // tiles whose first column is < col_scale_limit are multiplied by col_scale
   int col_scale_limit;      // (multiple of 256)
+#ifdef SYL_DIAG
+  long long* trace;         // timeline probe (tools/gemm_trace.py): CTA 0 writes clock64 stamps, slots in gemm3_tc.cuh
+#endif
 };
+
+// Timeline probe of the GEMM kernel, diagnostic build only: CTA 0 (leader of cluster 0) stamps clock64 into
+// p.trace[slot].  Slots: 0 globaltimer at entry, 1 entry, 2 prologue done, 3 first TMA issued, 8 + 3 t + {0, 1, 2} MMA
+// thread, tile t: accumulator free / first operands landed / last MMA committed, 64 + 2 t + {0, 1} epilogue warp 4, tile t:
+// accumulator complete / last store committed, 100 stores complete, 101 exit, 102 globaltimer at exit.
+#ifdef SYL_DIAG
+#define GEMM_TRACE(p, slot)                                                                  \
+  do {                                                                                       \
+    if ((p).trace != nullptr && blockIdx.x == 0 && (slot) < 128) (p).trace[(slot)] = clock64(); \
+  } while (0)
+#define GEMM_TRACE_NS(p, slot)                                                               \
+  do {                                                                                       \
+    if ((p).trace != nullptr && blockIdx.x == 0) {                                           \
+      unsigned long long t_;                                                                 \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                 \
+      (p).trace[(slot)] = (long long)t_;                                                     \
+    }                                                                                        \
+  } while (0)
+#else
+#define GEMM_TRACE(p, slot) do { } while (0)
+#define GEMM_TRACE_NS(p, slot) do { } while (0)
+#endif
 
 }  // namespace syl

@@ -128,7 +128,7 @@ def test_product_library_has_no_diagnostics(lib):
     """Experiment switches and diagnostic entry points live only in the -DSYL_DIAG build (ADVICE / VERDICT round 1):
     the product library exports none of them and its sources read the environment only inside `#ifdef SYL_DIAG`."""
     diag_only = set(_declared_functions(diag=True)) - set(_declared_functions())
-    assert diag_only == set(_lib.DIAG_SIGNATURES) == {"syl_attention_trace", "syl_mma_probe"}
+    assert diag_only == set(_lib.DIAG_SIGNATURES) == {"syl_attention_trace", "syl_mma_probe", "syl_gemm_set_trace"}
     for n in diag_only:
         assert not hasattr(lib, n), n
     csrc = os.path.join(ROOT, "sylber_b200", "csrc")
