@@ -1000,7 +1000,7 @@ int run_segment(const float* states, int B, int T, float thr_norm, float thr_mer
   launch_pdl(frame_sqnorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, states, rows, T, thr_norm, nsq, pw, scratch);
   launch_pdl(segment_kernel, dim3((T + SEG_CHUNK - 1) / SEG_CHUNK, B), dim3(SEG_SCAN_THREADS), 0, st, states, pw, T, thr_merge, seg,
              seg_count, max_seg, scratch);
-  if (seg_feat) launch_pdl(segment_pool_kernel, dim3(max_seg, B), dim3(192), 0, st, states, T, seg, seg_count, max_seg, seg_feat);
+  if (seg_feat) launch_pdl(segment_pool_kernel, dim3(std::min(max_seg, SEG_POOL_GRID), B), dim3(192), 0, st, states, T, seg, seg_count, max_seg, seg_feat);
   return launch_ok() ? SYL_OK : SYL_E_CUDA;
 }
 

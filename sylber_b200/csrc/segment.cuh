@@ -14,7 +14,7 @@
 // depends on the running centroid), but runs are independent of each other: a masked-off frame resets the scan state
 // (segment_utils.py:83-89), a mid-boundary only ever joins two segments of one run, and the refinement window stays
 // inside those two segments (:110-128).  So the work item is a run, not an utterance: CTA (c, b) owns the runs of
-// utterance b that START in frames [32 c, 32 c + 32) and follows the last of them to its end; the segments of a CTA go
+// utterance b that START in frames [16 c, 16 c + 16) (SEG_CHUNK) and follows the last of them to its end; the segments of a CTA go
 // to slots (first run start + k) of a frame-indexed table, which cannot collide with another CTA's because a segment has
 // at least one frame; the last CTA of an utterance to finish compacts the table in frame order (segment_utils.py:130).
 // One run spanning the whole utterance costs what the one-CTA-per-utterance kernel did; speech (pauses) and the synthetic
@@ -198,7 +198,7 @@ __device__ __forceinline__ void lane_mean_rows(LaneVec& acc, const float* __rest
 }
 
 // ----------------------------------------------------------------------------------------------
-// segmentation: grid (ceil(T / 32), B) - CTA (c, b) owns the runs of utterance b that start in frames [32 c, 32 c + 32).
+// segmentation: grid (ceil(T / SEG_CHUNK), B) - CTA (c, b) owns the runs of utterance b that start in its chunk of frames.
 //   states  [B, T, 768] fp32           pw [B, T]  from frame_sqnorm_kernel (sign = norm-threshold decision)
 //   seg     [B, max_seg, 2] int32 out  seg_count [B] out
 //   scratch [B, 6*(T+1)] int32/float workspace, six arrays of T + 1 per utterance:
@@ -209,7 +209,12 @@ __device__ __forceinline__ void lane_mean_rows(LaneVec& acc, const float* __rest
 //     sim_prev, sim_next  sweep cosines, indexed by frame (the window lies inside the CTA's own runs)
 // ----------------------------------------------------------------------------------------------
 constexpr int SEG_SCAN_THREADS = 96;     // warps 0, 1: the scan; warp 2: one thread that keeps the row ring full
-constexpr int SEG_CHUNK = 32;            // run starts per CTA: one ballot
+#ifndef SYL_SEG_CHUNK
+#define SYL_SEG_CHUNK 16
+#endif
+constexpr int SEG_CHUNK = SYL_SEG_CHUNK;  // frames whose run starts a CTA owns (one ballot, <= 32).  Measured stage time at
+                                          // 32 x 10 s / 8 x 60 s: 32 -> 0.084 / 0.109 ms, 16 -> 0.074 / 0.106, 8 -> 0.074 / 0.115
+static_assert(SEG_CHUNK >= 1 && SEG_CHUNK <= 32, "one lane per frame of the chunk");
 
 __global__ void __launch_bounds__(SEG_SCAN_THREADS)
 segment_kernel(const float* __restrict__ states_all, const float* __restrict__ pw_all, int T, float thr_merge,
@@ -242,7 +247,7 @@ segment_kernel(const float* __restrict__ states_all, const float* __restrict__ p
   int f0 = 0, f1 = 0;
   {
     const int i = c0 + lane;
-    const bool start = i < T && pw[i] > 0.0f && !(i > 0 && pw[i - 1] > 0.0f);
+    const bool start = lane < SEG_CHUNK && i < T && pw[i] > 0.0f && !(i > 0 && pw[i - 1] > 0.0f);
     const unsigned m = __ballot_sync(0xffffffffu, start);
     if (m != 0u) {
       f0 = c0 + __ffs(m) - 1;
@@ -504,37 +509,42 @@ segment_kernel(const float* __restrict__ states_all, const float* __restrict__ p
 
 // ----------------------------------------------------------------------------------------------
 // segment features (sylber.py:133): mean of the hidden states over each segment, NumPy order.
-// grid (max_seg, B), block 192: each thread owns 4 consecutive features.
+// grid (min(max_seg, SEG_POOL_GRID), B), block 192: each thread owns 4 consecutive features; a block walks the segments
+// sidx, sidx + gridDim.x, ... (a grid of max_seg blocks per utterance spent most of its time launching blocks without a segment).
 // ----------------------------------------------------------------------------------------------
+constexpr int SEG_POOL_GRID = 128;
+
 __global__ void __launch_bounds__(192)
 segment_pool_kernel(const float* __restrict__ states_all, int T, const int32_t* __restrict__ seg_all,
                     const int32_t* __restrict__ seg_count, int max_seg, float* __restrict__ feat_all) {
   griddep_launch_dependents();
   griddep_wait();
-  const int b = blockIdx.y, sidx = blockIdx.x;
-  if (sidx >= min(seg_count[b], max_seg)) return;
-  const int s = seg_all[((size_t)b * max_seg + sidx) * 2], e = seg_all[((size_t)b * max_seg + sidx) * 2 + 1];
+  const int b = blockIdx.y;
+  const int n = min(seg_count[b], max_seg);
   const float* st = states_all + (size_t)b * T * SEG_D + threadIdx.x * 4;
-  float4 acc;
-  if (e <= s) {
-    const float nan = __int_as_float(0x7fc00000);
-    acc = make_float4(nan, nan, nan, nan);
-  } else {
-    acc = *reinterpret_cast<const float4*>(st + (size_t)s * SEG_D);
-    for (int r = s + 1; r < e; ++r) {
-      const float4 x = *reinterpret_cast<const float4*>(st + (size_t)r * SEG_D);
-      acc.x = __fadd_rn(acc.x, x.x);
-      acc.y = __fadd_rn(acc.y, x.y);
-      acc.z = __fadd_rn(acc.z, x.z);
-      acc.w = __fadd_rn(acc.w, x.w);
+  for (int sidx = blockIdx.x; sidx < n; sidx += gridDim.x) {
+    const int s = seg_all[((size_t)b * max_seg + sidx) * 2], e = seg_all[((size_t)b * max_seg + sidx) * 2 + 1];
+    float4 acc;
+    if (e <= s) {
+      const float nan = __int_as_float(0x7fc00000);
+      acc = make_float4(nan, nan, nan, nan);
+    } else {
+      acc = *reinterpret_cast<const float4*>(st + (size_t)s * SEG_D);
+      for (int r = s + 1; r < e; ++r) {
+        const float4 x = *reinterpret_cast<const float4*>(st + (size_t)r * SEG_D);
+        acc.x = __fadd_rn(acc.x, x.x);
+        acc.y = __fadd_rn(acc.y, x.y);
+        acc.z = __fadd_rn(acc.z, x.z);
+        acc.w = __fadd_rn(acc.w, x.w);
+      }
+      const float fn = (float)(e - s);
+      acc.x = __fdiv_rn(acc.x, fn);
+      acc.y = __fdiv_rn(acc.y, fn);
+      acc.z = __fdiv_rn(acc.z, fn);
+      acc.w = __fdiv_rn(acc.w, fn);
     }
-    const float fn = (float)(e - s);
-    acc.x = __fdiv_rn(acc.x, fn);
-    acc.y = __fdiv_rn(acc.y, fn);
-    acc.z = __fdiv_rn(acc.z, fn);
-    acc.w = __fdiv_rn(acc.w, fn);
+    *reinterpret_cast<float4*>(feat_all + ((size_t)b * max_seg + sidx) * SEG_D + threadIdx.x * 4) = acc;
   }
-  *reinterpret_cast<float4*>(feat_all + ((size_t)b * max_seg + sidx) * SEG_D + threadIdx.x * 4) = acc;
 }
 
 }  // namespace syl

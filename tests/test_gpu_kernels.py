@@ -127,7 +127,7 @@ def _speechy(rng, T, on_mask):
 
 
 def test_segmentation_run_structure(lib, cuda):
-    """The scan is parallel over runs (stretches of frames above the norm threshold), one CTA per 32-frame chunk of run
+    """The scan is parallel over runs (stretches of frames above the norm threshold), one CTA per 16-frame chunk of run
     starts (segment.cuh): runs that start / end exactly on chunk borders, one run through every chunk, runs longer than a
     chunk behind short ones, T a multiple of 32 and not, a run reaching the last frame."""
     rng = np.random.default_rng(21)
@@ -135,11 +135,11 @@ def test_segmentation_run_structure(lib, cuda):
     for T in (32, 33, 64, 499, 1000):
         on = np.ones(T, bool)
         cases.append((T, on.copy()))                       # one run: every CTA but the first has nothing to do
-        on = np.ones(T, bool); on[31::32] = False           # every run ends on the last frame of a chunk
+        on = np.ones(T, bool); on[15::16] = False           # every run ends on the last frame of a chunk
         cases.append((T, on.copy()))
-        on = np.ones(T, bool); on[0::32] = False            # every run starts on frame 1 of a chunk
+        on = np.ones(T, bool); on[0::16] = False            # every run starts on frame 1 of a chunk
         cases.append((T, on.copy()))
-        on = np.ones(T, bool); on[32::32] = False; on[0] = False
+        on = np.ones(T, bool); on[16::16] = False; on[0] = False
         cases.append((T, on.copy()))
         on = rng.random(T) < 0.85                           # the bench's occupancy: short runs
         cases.append((T, on.copy()))

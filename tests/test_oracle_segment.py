@@ -120,7 +120,7 @@ def test_against_live_reference():
 
 
 # ------------------------------------------------------------------------------------------------
-# The CUDA scan is parallel over RUNS (csrc/segment.cuh): CTA c owns the runs that start in frames [32 c, 32 c + 32),
+# The CUDA scan is parallel over RUNS (csrc/segment.cuh): CTA c owns the runs that start in frames [16 c, 16 c + 16),
 # keeps its k-th segment in slot (first run start + k) of a frame-indexed table, and the table is packed in frame
 # order.  This CPU model of that decomposition (the oracle applied to each CTA's frame range) must equal the oracle
 # on the whole utterance: it is the property the kernel's structure rests on (segment_utils.py:83-89: a masked-off
@@ -153,7 +153,7 @@ def _run_parallel_model(states, norm_thr, merge_thr, chunk):
     return np.stack([slot_s[keep], slot_e[keep]], 1)
 
 
-@pytest.mark.parametrize("chunk", [4, 32])
+@pytest.mark.parametrize("chunk", [4, 16, 32])
 def test_runs_are_independent(chunk):
     rng = np.random.default_rng(5)
     for _ in range(60):
