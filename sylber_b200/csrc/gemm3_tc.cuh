@@ -201,7 +201,6 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
     const int lane = (int)lane_id();
     const int epi_tid = threadIdx.x - GEMM_EPI_WARP0 * 32;   // 0..511
     uint8_t* stage_buf = smem_epi + ew * GEMM3_EPI_STAGE_BYTES;      // 2 KB
-    const uint32_t stage_u32 = smem_u32(stage_buf);
     const int sw64 = (lane >> 1) & 3;        // 64-byte rows, SWIZZLE_64B: 16-byte chunk index ^ ((row >> 1) & 3)
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -219,6 +218,10 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
       const int warp_row0 = m_in_batch * 2 * GEMM_BLOCK_M + (int)cta_rank * GEMM_BLOCK_M + quarter * 32;
       const int row_in_batch = warp_row0 + lane;
       const bool warp_ok = warp_row0 < p.rows_per_batch;
+      // The cluster's LAST tile: its epilogue is the exposed tail of the launch (tools/gemm_trace.py: ~4 200 cycles, most of
+      // them the four serial "store has finished reading the staging buffer" waits), and the main loop's operand ring is
+      // idle by then - every step gets its own 2 KB of it (16 warps x 4 steps = 128 KB of the 192 KB) and never waits.
+      const bool last_tile = tile + num_clusters >= total_tiles;
       const bool zero_row = p.valid_rows != nullptr && row_in_batch >= __ldg(p.valid_rows + batch);
       const float scale = (n_tile * GEMM_BLOCK_N < p.col_scale_limit) ? p.col_scale : 1.0f;
       // stage this tile's bias (pre-multiplied by the column scale, a power of two) in shared memory, double
@@ -238,6 +241,10 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
         if (s + 1 < 4) tmem_ld_32x32b_x16(taddr0 + (s + 1) * 16, r[(s + 1) & 1]);   // prefetch the next 16 columns
+        // staging buffer of this step (hi-only output: steps 2 k and 2 k + 1 fill one buffer)
+        uint8_t* const sbuf = last_tile ? smem + (ew * 4 + s) * GEMM3_EPI_STAGE_BYTES : stage_buf;
+        uint8_t* const sbuf2 = last_tile ? smem + (ew * 4 + (s & ~1)) * GEMM3_EPI_STAGE_BYTES : stage_buf;
+        const uint32_t sbuf_u32 = smem_u32(sbuf), sbuf2_u32 = smem_u32(sbuf2);
         const int col0 = n_tile * GEMM_BLOCK_N + cb * 64 + s * 16;
         float v[16];
         const float4* b4 = reinterpret_cast<const float4*>(sbias + cb * 64 + s * 16);
@@ -261,15 +268,15 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
         if (warp_ok) {
           if (p.out_f32) {
             // 16 fp32 columns = 64-byte rows, 2 KB: box {16, 32}, SWIZZLE_64B
-            acquire();
+            if (!last_tile) acquire();
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              st_shared_v4(stage_u32 + lane * 64 + ((i ^ sw64) << 4), __float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]),
+              st_shared_v4(sbuf_u32 + lane * 64 + ((i ^ sw64) << 4), __float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]),
                            __float_as_uint(v[4 * i + 2]), __float_as_uint(v[4 * i + 3]));
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_3d(&o_f32, stage_buf, col0, warp_row0, batch);
+              tma_store_3d(&o_f32, sbuf, col0, warp_row0, batch);
               tma_store_commit();
             }
           }
@@ -278,15 +285,15 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
             uint32_t hi[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) hi[i] = pack_f16x2_sat(v[2 * i], v[2 * i + 1]);
-            if ((s & 1) == 0) acquire();
+            if ((s & 1) == 0 && !last_tile) acquire();
             const int c0 = (s & 1) * 2;                        // 16-byte chunk of the 64-byte row
-            st_shared_v4(stage_u32 + lane * 64 + (((c0 + 0) ^ sw64) << 4), hi[0], hi[1], hi[2], hi[3]);
-            st_shared_v4(stage_u32 + lane * 64 + (((c0 + 1) ^ sw64) << 4), hi[4], hi[5], hi[6], hi[7]);
+            st_shared_v4(sbuf2_u32 + lane * 64 + (((c0 + 0) ^ sw64) << 4), hi[0], hi[1], hi[2], hi[3]);
+            st_shared_v4(sbuf2_u32 + lane * 64 + (((c0 + 1) ^ sw64) << 4), hi[4], hi[5], hi[6], hi[7]);
             if ((s & 1) == 1) {
               fence_proxy_async_smem();
               __syncwarp();
               if (lane == 0) {
-                tma_store_3d(&o_hi, stage_buf, col0 - 16, warp_row0, batch);
+                tma_store_3d(&o_hi, sbuf2, col0 - 16, warp_row0, batch);
                 tma_store_commit();
               }
             }
@@ -300,18 +307,19 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
 #pragma unroll
               for (int i = 0; i < 8; ++i) hi[i] = pack_f16x2_sat(v[2 * i], v[2 * i + 1]);
             }
-            acquire();
-            st_shared_v4(stage_u32 + lane * 32, hi[0], hi[1], hi[2], hi[3]);
-            st_shared_v4(stage_u32 + lane * 32 + 16, hi[4], hi[5], hi[6], hi[7]);
+            // (next to an fp32 destination the fp32 store of this step has just been issued from sbuf: wait for it)
+            if (!last_tile || p.out_f32) acquire();
+            st_shared_v4(sbuf_u32 + lane * 32, hi[0], hi[1], hi[2], hi[3]);
+            st_shared_v4(sbuf_u32 + lane * 32 + 16, hi[4], hi[5], hi[6], hi[7]);
             if (p.out_lo) {
-              st_shared_v4(stage_u32 + 1024 + lane * 32, lo[0], lo[1], lo[2], lo[3]);
-              st_shared_v4(stage_u32 + 1024 + lane * 32 + 16, lo[4], lo[5], lo[6], lo[7]);
+              st_shared_v4(sbuf_u32 + 1024 + lane * 32, lo[0], lo[1], lo[2], lo[3]);
+              st_shared_v4(sbuf_u32 + 1024 + lane * 32 + 16, lo[4], lo[5], lo[6], lo[7]);
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_3d(&o_hi, stage_buf, col0, warp_row0, batch);
-              if (p.out_lo) tma_store_3d(&o_lo, stage_buf + 1024, col0, warp_row0, batch);
+              tma_store_3d(&o_hi, sbuf, col0, warp_row0, batch);
+              if (p.out_lo) tma_store_3d(&o_lo, sbuf + 1024, col0, warp_row0, batch);
               tma_store_commit();
             }
           }
