@@ -371,6 +371,11 @@ def run_ours(args):
     eng = seg._engine
     lens = [c.shape[1] for c in clips]
     flops, T, L = stage_flops(pad_to, layers)           # executed work: every clip is padded to pad_to
+    if args.trim:
+        # trimmed mode computes only an utterance's own frames (keys are masked to them already): the executed work per
+        # clip is that of its own length, averaged here so that `flops[stage] * B` stays the step's total
+        per_clip = [stage_flops(n, layers)[0] for n in lens]
+        flops = {k: sum(f[k] for f in per_clip) / len(per_clip) for k in flops}
     frames_valid_local = valid_frames(clips)
     thr_n, thr_m = np.float32(THR_NORM), np.float32(THR_MERGE)
 
@@ -447,6 +452,29 @@ def run_ours(args):
     eng.profile(False)
     value = frames_valid * args.steps / (ms_total / 1e3)
     seg_counts = torch.cat([o[2] for o in out]).cpu().numpy()
+
+    # The attention + MLP path inside the CUDA-graph replay (the launch mode `value` is measured in): the forward without
+    # segmentation at all encoder layers minus the same forward at 0 layers = what the layers add to the step.  The stage
+    # timers above bracket eager launches with events, which adds ~10 us of idle per kernel to every stage they report.
+    def graph_forward_ms(active):
+        eng.set_active_layers(active)
+        f = lambda: [eng.forward(w, n, thr_n, thr_m, segment=False, slot=("bench_enc", k)) for k, (w, n) in enumerate(subs)]
+        for _ in range(3):
+            f()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        g0.record()
+        for _ in range(args.steps):
+            f()
+        g1.record()
+        torch.cuda.synchronize()
+        return g0.elapsed_time(g1) / args.steps
+    enc_graph_ms = None
+    if rank == 0:
+        t_all = graph_forward_ms(layers)
+        t_none = graph_forward_ms(0)
+        enc_graph_ms = t_all - t_none
+    eng.set_active_layers(layers)
 
     # ---------------- end-to-end through the public call, from pinned host tensors to NumPy results ----------------
     def e2e_call():
@@ -574,7 +602,15 @@ def run_ours(args):
                           "ms_per_step": round(encln_ms, 4),
                           "what": "QKV + attention + out-proj + FFN1 + FFN2 + the two LayerNorms of every encoder layer",
                           "without_layernorms": {"achieved": round(enc_tf, 1), "frac": round(enc_tf / peaks["tf_sustained"], 4),
-                                                 "ms_per_step": round(enc_ms, 4)}},
+                                                 "ms_per_step": round(enc_ms, 4)},
+                          "timing": "per-stage CUDA events around EAGER launches (a profiled pass after the timed region)"},
+        "attn_mlp_path_in_graph": {
+            "achieved": round(sum(flops[s_] for s_ in ENC_STAGES if s_ in flops) * B / (enc_graph_ms * 1e-3) / 1e12, 1),
+            "frac": round(sum(flops[s_] for s_ in ENC_STAGES if s_ in flops) * B / (enc_graph_ms * 1e-3) / 1e12 / peaks["tf_sustained"], 4),
+            "unit": "TFLOP/s", "ms_per_step": round(enc_graph_ms, 4),
+            "what": "the same path (LayerNorms included) as the CUDA-graph replay runs it: device time of the forward at all "
+                    "encoder layers minus the forward at 0 layers, no segmentation in either - the launch mode `value` is "
+                    "measured in"} if enc_graph_ms else None,
         "step": {"achieved": round(step_tf, 1), "frac": round(step_tf / peaks["tf_sustained"], 4), "unit": "TFLOP/s",
                  "what": "all algorithmic FLOPs of the step / device-resident step time (segmentation, LayerNorms, conv0 included in the time)"},
         "attention_hbm": {"achieved": stages.get("attention", {}).get("hbm_gbs"), "peak": peaks["hbm_gbs"], "unit": "GB/s",
