@@ -7,7 +7,7 @@ import torch
 
 import gpu_util as G
 from oracle import segment_ref as R
-from seg_cases import plateau_states
+from seg_cases import long_segment_states, plateau_states
 
 pytestmark = pytest.mark.gpu
 
@@ -150,6 +150,18 @@ def test_segmentation_run_structure(lib, cuda):
     for T, on in cases:
         st = _speechy(rng, T, on)[None]
         _check_segmentation(lib, cuda, st)
+
+
+@pytest.mark.parametrize("kind", ["alternate", "tail", "drift"])
+def test_segmentation_long_segments(lib, cuda, kind):
+    """Refinement over LONG segments: means of 35-400 rows and sweep windows of 30-200 frames come through the
+    shared-memory row ring (segment.cuh, SEG_STREAM_MIN) - same arithmetic, so still bit-identical to the oracle; "drift"
+    takes the merge branch, the others the sweep."""
+    rng = np.random.default_rng({"alternate": 41, "tail": 42, "drift": 43}[kind])
+    for T in (300, 700, 1200):
+        st = np.stack([long_segment_states(rng, T, kind) for _ in range(2)])
+        cnt = _check_segmentation(lib, cuda, st)
+        assert cnt.min() >= 1
 
 
 def test_segmentation_reuses_workspace(lib, cuda):
