@@ -7,7 +7,7 @@ sd = syllabic_test_state_dict(9, 0, SPEECH_LIKE_BIAS_NORM)
 g = torch.Generator().manual_seed(1)
 wav = torch.randn(32, 160000, generator=g).pin_memory()
 wl = [wav[i:i+1] for i in range(32)]
-for split in ([11, 11, 10], [12, 12, 8], [14, 12, 6], [8, 12, 12], [6, 10, 10, 6]):
+for split in ([8, 12, 12], [12, 12, 8], [10, 12, 10], [12, 20], [16, 16], [8, 24], [8, 12, 12]):
     seg = Segmenter(model_ckpt=None, state_dict=sd, device="cuda:0", streams=len(split), sub_batch_sizes=split, max_batch=32)
     for _ in range(4): seg(wav=wl)
     torch.cuda.synchronize(); t0 = time.perf_counter()
