@@ -624,6 +624,8 @@ int launch_gemm3_raw(const GemmOp& op, const CUtensorMap& b_hi, const CUtensorMa
 #ifdef SYL_DIAG
   GemmParams p = op.p;
   p.trace = g_gemm_trace;
+  static const int epi_skip = diag_env("SYL_GEMM_EPI_SKIP", 0);
+  p.epi_skip = epi_skip;
 #else
   const GemmParams& p = op.p;
 #endif

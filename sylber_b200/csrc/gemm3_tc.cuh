@@ -234,6 +234,20 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
       if (ew == 0 && lane == 0) GEMM_TRACE(p, 64 + 2 * it);
+#ifdef SYL_DIAG
+      if (p.epi_skip & 2) {      // timing experiment: the accumulator is released unread
+        tc_fence_before_sync();
+        __syncwarp();
+        if (ew == 0 && lane == 0) GEMM_TRACE(p, 65 + 2 * it);
+        if (lane == 0) mbar_arrive_remote(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        ++it;
+        continue;
+      }
+#endif
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * GEMM_BLOCK_N + cb * 64);
       uint32_t r[2][16];
       tmem_ld_32x32b_x16(taddr0, r[0]);
@@ -265,6 +279,12 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = 0.0f;
         }
+#ifdef SYL_DIAG
+        if (p.epi_skip & 1) {    // timing experiment: TMEM is read and the epilogue math done, nothing is staged or stored
+#pragma unroll
+          for (int i = 0; i < 16; ++i) asm volatile("" ::"f"(v[i]));
+        } else
+#endif
         if (warp_ok) {
           if (p.out_f32) {
             // 16 fp32 columns = 64-byte rows, 2 KB: box {16, 32}, SWIZZLE_64B
@@ -275,7 +295,11 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant_
                            __float_as_uint(v[4 * i + 2]), __float_as_uint(v[4 * i + 3]));
             fence_proxy_async_smem();
             __syncwarp();
+#ifdef SYL_DIAG
+            if (lane == 0 && !(p.epi_skip & 4)) {  // 4 = timing experiment: staged in shared memory, never stored
+#else
             if (lane == 0) {
+#endif
               tma_store_3d(&o_f32, sbuf, col0, warp_row0, batch);
               tma_store_commit();
             }

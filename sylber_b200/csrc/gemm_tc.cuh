@@ -40,6 +40,7 @@ struct GemmParams {
   int col_scale_limit;      // (multiple of 256)
 #ifdef SYL_DIAG
   long long* trace;         // timeline probe (tools/gemm_trace.py): CTA 0 writes clock64 stamps, slots in gemm3_tc.cuh
+  int epi_skip;             // SYL_GEMM_EPI_SKIP (timing experiments, wrong results): 1 = no staging / stores, 2 = no epilogue work at all
 #endif
 };
 
